@@ -1,0 +1,251 @@
+// Kernel family (c): per-ray stratified sampling, alpha compositing, inverse-CDF importance
+// sampling, depth-guided samples and the per-ray sort  (src/render/nerf.py:98-161, 178-244, 286-295).
+// One warp per ray; every array is (B, K) fp32 row-major so a warp reads/writes 128 B lines.
+// All arithmetic is fp32 with the reference's operation order; products/sums that torch performs
+// as separate ops use __fmul_rn/__fadd_rn so the compiler cannot contract them into FMAs.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace pnr {
+
+__device__ __forceinline__ float lerp_depth(float near, float far, float s, int lindisp) {
+  if (!lindisp)  // near*(1-s) + far*s            nerf.py:113, 145
+    return __fadd_rn(__fmul_rn(near, __fsub_rn(1.f, s)), __fmul_rn(far, s));
+  // 1 / (1/near*(1-s) + 1/far*s)                  nerf.py:115, 147
+  float a = __fmul_rn(__fdiv_rn(1.f, near), __fsub_rn(1.f, s));
+  float b = __fmul_rn(__fdiv_rn(1.f, far), s);
+  return __fdiv_rn(1.f, __fadd_rn(a, b));
+}
+
+// ---- sample_coarse ----------------------------------------------------------------------------
+__global__ void sample_coarse_kernel(const float* __restrict__ rays, const float* __restrict__ jitter, long long n,
+                                     int Kc, int lindisp, float lin_end, float lin_step, float step,
+                                     float* __restrict__ z) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long r = i / Kc;
+  int k = (int)(i - r * Kc);
+  // torch.linspace(0, 1-step, Kc): first half start + step*k, second half end - step*(Kc-1-k)
+  float s = (k < Kc / 2) ? __fmul_rn(lin_step, (float)k) : __fsub_rn(lin_end, __fmul_rn(lin_step, (float)(Kc - 1 - k)));
+  s = __fadd_rn(s, __fmul_rn(jitter[i], step));
+  z[i] = lerp_depth(rays[r * 8 + 6], rays[r * 8 + 7], s, lindisp);
+}
+
+int launch_sample_coarse(const float* rays, const float* jitter, int B, int Kc, int lindisp, float* z,
+                         cudaStream_t st) {
+  long long n = (long long)B * Kc;
+  if (n == 0) return PNR_OK;
+  float step = (float)(1.0 / Kc);
+  float lin_end = (float)(1.0 - 1.0 / Kc);
+  float lin_step = Kc > 1 ? lin_end / (float)(Kc - 1) : 0.f;
+  sample_coarse_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(rays, jitter, n, Kc, lindisp, lin_end, lin_step,
+                                                                     step, z);
+  PNR_LAUNCHED();
+  return PNR_OK;
+}
+
+// ---- composite --------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+composite_kernel(const float* __restrict__ rays, const float* __restrict__ z, const float4* __restrict__ out4, int B,
+                 int K, int white, float* __restrict__ weights, float* __restrict__ rgb, float* __restrict__ depth) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= B) return;
+  const float far = rays[(size_t)r * 8 + 7];
+  const float* zr = z + (size_t)r * K;
+  const float4* o4 = out4 + (size_t)r * K;
+  float carry = 1.f;  // T at the start of this 32-sample chunk
+  float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aw = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    int k = k0 + lane;
+    bool ok = k < K;
+    float zk = ok ? zr[k] : 0.f;
+    float zn = (k + 1 < K) ? zr[k + 1] : far;  // last delta = far - z_K      nerf.py:181
+    float4 o = ok ? o4[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float delta = __fsub_rn(zn, zk);
+    // alpha = 1 - exp(-delta * relu(sigma))                                   nerf.py:228
+    float alpha = ok ? __fsub_rn(1.f, expf(-__fmul_rn(delta, fmaxf(o.w, 0.f)))) : 0.f;
+    float f = ok ? __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f) : 1.f;  // 1 - alpha + 1e-10   :230
+    // inclusive product scan over the chunk
+    float p = f;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      float q = __shfl_up_sync(0xffffffffu, p, off);
+      if (lane >= off) p = __fmul_rn(p, q);
+    }
+    float excl = __shfl_up_sync(0xffffffffu, p, 1);
+    if (lane == 0) excl = 1.f;
+    float T = __fmul_rn(carry, excl);  // cumprod([1, f_0, f_1, ...])[k]           :231-234
+    float w = __fmul_rn(alpha, T);     // weights = alpha * T[:-1]                  :235
+    carry = __fmul_rn(carry, __shfl_sync(0xffffffffu, p, 31));
+    if (ok) {
+      if (weights) weights[(size_t)r * K + k] = w;
+      ar += w * o.x;
+      ag += w * o.y;
+      ab += w * o.z;
+      ad += w * zk;
+      aw += w;
+    }
+  }
+  ar = warp_sum(ar);
+  ag = warp_sum(ag);
+  ab = warp_sum(ab);
+  ad = warp_sum(ad);
+  aw = warp_sum(aw);
+  if (lane == 0) {
+    if (white) {  // rgb + 1 - pix_alpha                                          :241-244
+      ar = ar + 1.f - aw;
+      ag = ag + 1.f - aw;
+      ab = ab + 1.f - aw;
+    }
+    rgb[(size_t)r * 3 + 0] = ar;
+    rgb[(size_t)r * 3 + 1] = ag;
+    rgb[(size_t)r * 3 + 2] = ab;
+    depth[r] = ad;
+  }
+}
+
+int launch_composite(const float* rays, const float* z, const float* rgb_sigma, int B, int K, int white,
+                     float* weights, float* rgb, float* depth, cudaStream_t st) {
+  if (B == 0) return PNR_OK;
+  PNR_CHECK_ARG(K >= 1, "composite: K must be >= 1");
+  composite_kernel<<<ceil_div(B, 8), 256, 0, st>>>(rays, z, (const float4*)rgb_sigma, B, K, white, weights, rgb,
+                                                   depth);
+  PNR_LAUNCHED();
+  return PNR_OK;
+}
+
+// ---- inverse-CDF bin lookup ---------------------------------------------------------------------
+// searchsorted(cdf, u, right=True) - 1, clamped below at 0 only (nerf.py:138-139):
+// number of cdf entries <= u, minus one.  n entries, ascending.
+__device__ __forceinline__ float cdf_bin(const float* cdf, int n, float u) {
+  int lo = 0, hi = n;  // first index with cdf[idx] > u
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+  }
+  float ind = (float)lo - 1.f;
+  return fmaxf(ind, 0.f);
+}
+
+__global__ void fine_indices_kernel(const float* __restrict__ cdf, const float* __restrict__ u, long long n, int Kc,
+                                    int Kf, float* __restrict__ inds) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long r = i / Kf;
+  inds[i] = cdf_bin(cdf + r * (Kc + 1), Kc + 1, u[i]);
+}
+
+int launch_fine_indices(const float* cdf, const float* u, int B, int Kc, int Kf, float* inds, cudaStream_t st) {
+  long long n = (long long)B * Kf;
+  if (n == 0) return PNR_OK;
+  fine_indices_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(cdf, u, n, Kc, Kf, inds);
+  PNR_LAUNCHED();
+  return PNR_OK;
+}
+
+// ---- sample_fine + sample_fine_depth + cat + sort -------------------------------------------------
+// smem per warp: cdf[Kc+1] followed by the sort buffer [Kpad] (Kpad = next pow2 >= Kc + n_fine).
+__global__ void __launch_bounds__(256)
+sample_fine_sorted_kernel(const float* __restrict__ rays, const float* __restrict__ z_coarse,
+                          const float* __restrict__ weights, const float* __restrict__ depth,
+                          const float* __restrict__ fine_u, const float* __restrict__ fine_jit,
+                          const float* __restrict__ depth_nrm, int B, int Kc, int n_imp, int n_dep, float depth_std,
+                          int lindisp, int Kpad, float* __restrict__ z_out) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (r >= B) return;  // whole warp exits together
+  float* cdf = smem + (size_t)warp * (Kc + 1 + Kpad);
+  float* buf = cdf + Kc + 1;
+  const float near = rays[(size_t)r * 8 + 6], far = rays[(size_t)r * 8 + 7];
+  const int K = Kc + n_imp + n_dep;
+  // coarse samples go into the sort buffer; padding is +inf
+  for (int k = lane; k < Kpad; k += 32) buf[k] = k < Kc ? z_coarse[(size_t)r * Kc + k] : CUDART_INF_F;
+  if (n_imp > 0) {
+    // pdf = (w + 1e-5) / sum ; cdf = [0, cumsum(pdf)]                          nerf.py:129-133
+    float s = 0.f;
+    for (int k = lane; k < Kc; k += 32) {
+      float w = __fadd_rn(weights[(size_t)r * Kc + k], 1e-5f);
+      cdf[k + 1] = w;
+      s += w;
+    }
+    s = warp_sum(s);
+    __syncwarp();
+    if (lane == 0) {  // sequential cumsum, like torch.cumsum on one row
+      float c = 0.f;
+      cdf[0] = 0.f;
+      for (int k = 1; k <= Kc; ++k) {
+        c = __fadd_rn(c, __fdiv_rn(cdf[k], s));
+        cdf[k] = c;
+      }
+    }
+    __syncwarp();
+    for (int j = lane; j < n_imp; j += 32) {
+      float ind = cdf_bin(cdf, Kc + 1, fine_u[(size_t)r * n_imp + j]);
+      // z_steps = (inds + rand) / n_coarse                                     nerf.py:141
+      float zs = __fdiv_rn(__fadd_rn(ind, fine_jit[(size_t)r * n_imp + j]), (float)Kc);
+      buf[Kc + j] = lerp_depth(near, far, zs, lindisp);
+    }
+  }
+  if (n_dep > 0) {
+    float d = depth[r];
+    for (int j = lane; j < n_dep; j += 32) {
+      // clamp(depth + randn*depth_std, near, far)                              nerf.py:157-160
+      float zz = __fadd_rn(d, __fmul_rn(depth_nrm[(size_t)r * n_dep + j], depth_std));
+      buf[Kc + n_imp + j] = fmaxf(fminf(zz, far), near);
+    }
+  }
+  __syncwarp();
+  // bitonic sort of Kpad values, ascending
+  for (int size = 2; size <= Kpad; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = lane; t < (Kpad >> 1); t += 32) {
+        int i = 2 * t - (t & (stride - 1));  // index with bit 'stride' clear
+        int j = i + stride;
+        bool up = ((i & size) == 0);
+        float a = buf[i], b = buf[j];
+        if ((a > b) == up) {
+          buf[i] = b;
+          buf[j] = a;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  for (int k = lane; k < K; k += 32) z_out[(size_t)r * K + k] = buf[k];
+}
+
+int launch_sample_fine_sorted(const float* rays, const float* z_coarse, const float* weights, const float* depth,
+                              const float* fine_u, const float* fine_jitter, const float* depth_normal, int B,
+                              int Kc, int n_fine, int n_fine_depth, float depth_std, int lindisp, float* z_out,
+                              cudaStream_t st) {
+  if (B == 0) return PNR_OK;
+  int n_dep = n_fine_depth, n_imp = n_fine - n_fine_depth;
+  PNR_CHECK_ARG(n_imp >= 0 && n_dep >= 0, "sample_fine: n_fine (%d) must include n_fine_depth (%d)", n_fine, n_dep);
+  int K = Kc + n_fine;
+  int Kpad = 2;
+  while (Kpad < K) Kpad <<= 1;
+  PNR_UNSUPPORTED(Kpad > 2048, "sample_fine: more than 2048 samples per ray");
+  int wpb = 8;
+  size_t smem = (size_t)wpb * (Kc + 1 + Kpad) * sizeof(float);
+  while (smem > 48 * 1024 && wpb > 1) {
+    wpb >>= 1;
+    smem = (size_t)wpb * (Kc + 1 + Kpad) * sizeof(float);
+  }
+  PNR_UNSUPPORTED(smem > 48 * 1024, "sample_fine: per-ray sample count too large for shared memory");
+  sample_fine_sorted_kernel<<<ceil_div(B, wpb), wpb * 32, smem, st>>>(rays, z_coarse, weights, depth, fine_u,
+                                                                     fine_jitter, depth_normal, B, Kc, n_imp, n_dep,
+                                                                     depth_std, lindisp, Kpad, z_out);
+  PNR_LAUNCHED();
+  return PNR_OK;
+}
+
+}  // namespace pnr

@@ -45,3 +45,39 @@ def renderer_kwargs(conf, kw):
 
 def maxabs(a, b):
     return (a.double() - b.double()).abs().max().item()
+
+
+def build_product(case_name, device="cuda", precision="fp32"):
+    """This package's PixelNeRFNet + NeRFRenderer for a synthetic case, with the oracle Scene that
+    holds the same weights / feature maps / cameras."""
+    import pixel_nerf_multiscale_b200 as pk
+
+    conf = load_conf(case_name)
+    case = synth.CASES[case_name]
+    scene, raw = synth.build_case(case_name, conf["model"], device=device)
+    torch.manual_seed(0)
+    net = pk.make_model(conf["model"]).to(device).eval()
+    net.precision = precision
+    assert net.d_in == raw["d_in"] and net.latent_size == raw["d_latent"]
+    net.mlp_coarse.load_state_dict(raw["mlp_coarse"], strict=True)
+    net.mlp_fine.load_state_dict(raw["mlp_fine"], strict=True)
+    sb, ns, H, W = case["sb"], case["ns"], case["H"], case["W"]
+    images = torch.zeros(sb, ns, 3, H, W, device=device)
+    with torch.no_grad():
+        net.encode(images, raw["poses"].to(device), raw["focal"].to(device),
+                   c=None if raw["c"] is None else raw["c"].to(device))
+    net.encoder.latent = raw["latents"][-1]
+    net.encoder.latents = list(raw["latents"])
+    net.invalidate_scene()
+    return net, conf, scene, raw
+
+
+def make_renderer(conf, kw, eval_batch_size=50000):
+    import pixel_nerf_multiscale_b200 as pk
+    from pixel_nerf_multiscale_b200.util.conf import ConfigFactory as CF
+
+    rconf = CF.from_dict(conf["renderer"].to_dict())
+    for k in ("n_coarse", "n_fine", "n_fine_depth", "depth_std"):
+        if k in kw:
+            rconf.put(k, kw[k])
+    return pk.NeRFRenderer.from_conf(rconf, lindisp=kw.get("lindisp", False), eval_batch_size=eval_batch_size)

@@ -1,0 +1,150 @@
+"""
+GPU parity, fp32 validation mode: the CUDA path (through the C ABI) against the oracle on the
+same device and against the reference-generated goldens.  Tolerance (BASELINE.json north_star):
+per-pixel RGB/depth max-abs <= 1e-4 in fp32 mode.
+"""
+import pytest
+import torch
+
+from oracle import pixelnerf_oracle as po
+from oracle import synth
+from helpers import (N_POINTS, RENDER_SEED, build_product, load_golden, make_renderer, maxabs, renderer_kwargs,
+                     sample_points)
+
+pytestmark = pytest.mark.gpu
+CASES = ["ss_ns1", "ms_ns2", "dtu_ns3", "ms_ns3_sb2"]
+TOL = 1e-4
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_point_features_and_net_forward(name):
+    from pixel_nerf_multiscale_b200 import _native as N
+
+    gold = load_golden(name)
+    net, conf, scene, raw = build_product(name, precision="fp32")
+    case = synth.CASES[name]
+    xyz, vd = sample_points(case, case["sb"], N_POINTS, 7)
+    xyz, vd = xyz.cuda(), vd.cuda()
+    # kernel (a) alone: rows of the MLP input
+    sc, keep = net.native_scene()
+    rows = case["sb"] * case["ns"] * N_POINTS
+    zx = torch.empty(rows, raw["d_latent"] + raw["d_in"], device="cuda")
+    N.check(N.lib().pnr_point_features_f32(sc, N.ptr(xyz.contiguous()), N.ptr(vd.contiguous()), case["sb"], N_POINTS,
+                                           N.ptr(zx), N.stream_ptr(zx.device)), "features")
+    assert maxabs(zx.cpu(), gold["zx"]) < 2e-5
+    # kernels (a)+(b): PixelNeRFNet.forward, coarse and fine MLP
+    for coarse, key in ((True, "net_coarse"), (False, "net_fine")):
+        out = net(xyz, coarse=coarse, viewdirs=vd)
+        ref = po.net_forward(scene, xyz, coarse=coarse, viewdirs=vd)
+        assert out.shape == gold[key].shape
+        for other in (ref.cpu(), gold[key]):
+            assert maxabs(out[..., :3].cpu(), other[..., :3]) < TOL
+            assert torch.allclose(out[..., 3].cpu(), other[..., 3], rtol=1e-4, atol=1e-4)
+
+
+def test_mlp_rows_api():
+    """ResnetFC.forward on caller-provided rows (pnr_mlp_forward) vs oracle."""
+    net, conf, scene, raw = build_product("ms_ns2", precision="fp32")
+    torch.manual_seed(5)
+    ns, p = 2, 37
+    zx = torch.randn(ns * p, raw["d_latent"] + raw["d_in"], device="cuda")
+    from pixel_nerf_multiscale_b200 import _native as N
+
+    out = net.mlp_coarse(zx, combine_inner_dims=(ns, p), precision=N.FP32)
+    ref = po.resnetfc_forward(scene.mlp_coarse, zx, raw["d_latent"], 5, 3, (ns, p))
+    assert out.reshape(-1, 4).shape == ref.reshape(-1, 4).shape
+    assert torch.allclose(out.reshape(-1, 4), ref.reshape(-1, 4), rtol=1e-4, atol=1e-4)
+
+
+def _variants(name):
+    return [k[len("render_"):] for k in load_golden(name) if k.startswith("render_")]
+
+
+@pytest.mark.parametrize("name,variant", [(n, v) for n in CASES for v in _variants(n)])
+def test_render_vs_golden_and_oracle(name, variant):
+    gold = load_golden(name)["render_" + variant]
+    net, conf, scene, raw = build_product(name, precision="fp32")
+    case = synth.CASES[name]
+    sb = case["sb"]
+    rays = synth.target_rays(case, case["rays"], 3, sb).cuda()
+    kw = renderer_kwargs(conf, gold["kw"])
+    renderer = make_renderer(conf, gold["kw"])
+    # replay the reference's own random draws: CPU generator, same seed, same order
+    torch.manual_seed(RENDER_SEED)
+    tape = po.RngTape(rays.shape[0] * rays.shape[1], kw["n_coarse"], kw["n_fine"], kw["n_fine_depth"], "cpu")
+    tape.draw_coarse()
+    if kw["n_fine"] > 0:
+        tape.draw_fine()
+    cu = lambda t: None if t is None else t.cuda()
+    dtape = {k: v for k, v in dict(coarse=cu(tape.coarse), u=cu(tape.u), jitter=cu(tape.jit), normal=cu(tape.nrm)).items()
+             if v is not None}
+    renderer.rng_tape = dict(dtape)
+    res = renderer(net, rays, want_weights=True, taps=True)
+    assert torch.equal(res.coarse.z.reshape(-1, kw["n_coarse"]).cpu(), gold["z_coarse"])
+    for lvl in ("coarse", "fine"):
+        if lvl + "_rgb" not in gold:
+            assert lvl not in res
+            continue
+        assert maxabs(res[lvl].rgb.cpu(), gold[lvl + "_rgb"]) < TOL
+        assert maxabs(res[lvl].depth.cpu(), gold[lvl + "_depth"]) < TOL
+        assert maxabs(res[lvl].weights.cpu(), gold[lvl + "_weights"]) < TOL
+    if "z_fine" in gold:
+        assert maxabs(res.fine.z.reshape(gold["z_fine"].shape).cpu(), gold["z_fine"]) < 1e-5
+    # same thing through the generic (model-callable) path: per-ray kernels + model() calls
+    renderer.rng_tape = dict(dtape)
+    class Opaque:  # not a PixelNeRFNet instance -> generic path
+        use_viewdirs = net.use_viewdirs
+
+        def __call__(self, x, coarse=True, viewdirs=None):
+            return net(x, coarse=coarse, viewdirs=viewdirs)
+
+    renderer.eval_batch_size = 1500
+    res2 = renderer(Opaque(), rays, want_weights=True)
+    last = "fine" if "fine" in res else "coarse"
+    assert maxabs(res2[last].rgb, res[last].rgb) < 1e-5
+    assert maxabs(res2[last].depth, res[last].depth) < 1e-5
+
+
+def test_bind_parallel_wrapper_outputs():
+    net, conf, scene, raw = build_product("ss_ns1", precision="fp32")
+    case = synth.CASES["ss_ns1"]
+    rays = synth.target_rays(case, 50, 3, 1).cuda()
+    renderer = make_renderer(conf, {})
+    par = renderer.bind_parallel(net, [0], simple_output=True).eval()
+    torch.manual_seed(1)
+    rgb, depth = par(rays)
+    assert rgb.shape == (1, 50, 3) and depth.shape == (1, 50)
+    full = renderer.bind_parallel(net, None, simple_output=False).eval()
+    torch.manual_seed(1)
+    d = full(rays, want_weights=True)
+    assert set(d.keys()) == {"coarse", "fine"} and set(d["fine"].keys()) == {"rgb", "depth", "weights"}
+    assert torch.equal(d["fine"]["rgb"], rgb)
+    # empty batch guard (nerf.py:23-27)
+    e_rgb, e_depth = par(rays[:0])
+    assert e_rgb.shape == (0, 3) and e_depth.shape == (0,)
+
+
+def test_fine_indices_bit_exact_given_cdf():
+    """Importance-sample indices must be bit-exact given identical CDFs (north_star)."""
+    from pixel_nerf_multiscale_b200 import _native as N
+
+    torch.manual_seed(3)
+    B, Kc, Kf = 4096, 64, 16
+    w = torch.rand(B, Kc) ** 4
+    w[::7] = 0.0  # empty rays -> uniform cdf
+    cdf = po.fine_cdf(w)
+    u = torch.rand(B, Kf)
+    u[0, :4] = torch.tensor([0.0, 1.0 - 1e-7, cdf[0, 5].item(), cdf[0, 64].item()])  # ties / top edge
+    ref = po.fine_indices(cdf, u)
+    inds = torch.empty(B, Kf, device="cuda")
+    cd, ud = cdf.cuda().contiguous(), u.cuda().contiguous()
+    N.check(N.lib().pnr_fine_indices(N.ptr(cd), N.ptr(ud), B, Kc, Kf, N.ptr(inds), N.stream_ptr(inds.device)), "inds")
+    assert torch.equal(inds.cpu(), ref)
+
+
+def test_errors_are_loud():
+    net, conf, scene, raw = build_product("ss_ns1", precision="fp32")
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 4, 3), coarse=True, viewdirs=torch.zeros(1, 4, 3))  # CPU tensors: no fallback
+    with pytest.raises(AssertionError):
+        net.mlp_coarse(torch.zeros(8, 17, device="cuda"))  # wrong row width (resnetfc.py:190)
