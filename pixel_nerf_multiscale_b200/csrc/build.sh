@@ -7,10 +7,10 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr ${PNR_EXTRA_NVCC_FLAGS}"
 mkdir -p "$HERE/build"
 pids=()
-for f in api features mlp_f32 rays mlp_tc; do
+for f in api features mlp_f32 rays mlp_tc tc_probe; do
   ( $NVCC $FLAGS -c "$HERE/$f.cu" -o "$HERE/build/$f.o" ) &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$HERE"/build/{api,features,mlp_f32,rays,mlp_tc}.o -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$HERE"/build/{api,features,mlp_f32,rays,mlp_tc,tc_probe}.o -lcudart
 echo "built $OUT"
