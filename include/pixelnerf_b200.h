@@ -115,6 +115,18 @@ const char* pnr_last_error(void);
  * (bench.py's gpu_launches). */
 int64_t pnr_launch_count(int reset);
 
+/* Synchronises `stream` and reports (then clears) a pipeline fault recorded by the tensor-core
+ * kernels on the current device: their mbarrier waits are bounded, so a protocol error surfaces
+ * here as PNR_ERR_CUDA instead of hanging the GPU.  Debug / test aid; never needed for results. */
+int pnr_tc_check(pnr_stream stream);
+
+/* Optional per-kernel timing for the roofline report: between begin/end every tracked kernel is
+ * bracketed by CUDA events on its launching stream.  Arrays have 3 entries:
+ * [0] point-feature (gather) kernel, [1] MLP phase A (per point-view rows), [2] MLP phase B.
+ * flops/bytes are the ALGORITHMIC work of the tracked launches. */
+int pnr_profile_begin(void);
+int pnr_profile_end(double* ms, int64_t* launches, double* flops, double* bytes);
+
 /* ---- packing ------------------------------------------------------------------------- */
 /* NCHW fp32 feature map (encoder output, encoder.py:117-136) -> NHWC fp32|bf16.          */
 int pnr_pack_level(const float* src_nchw, int n_views, int C, int H, int W, void* dst_nhwc,

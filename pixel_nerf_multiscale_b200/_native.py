@@ -65,6 +65,9 @@ EXPORTS = {
     "pnr_abi_version": (_i, []),
     "pnr_last_error": (C.c_char_p, []),
     "pnr_launch_count": (C.c_int64, [_i]),
+    "pnr_tc_check": (_i, [_fp]),
+    "pnr_profile_begin": (_i, []),
+    "pnr_profile_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "pnr_pack_level": (_i, [_fp, _i, _i, _i, _i, _fp, _i, _fp]),
     "pnr_mlp_packed_bytes": (_sz, [_PM]),
     "pnr_mlp_pack_bf16": (_i, [_PM, _fp, _sz, _fp]),

@@ -2,6 +2,8 @@
 // PixelNeRFNet.forward (models.py.backup2:155-282) and one NeRFRenderer.forward (nerf.py:251-303).
 #include <stdarg.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace pnr {
@@ -21,10 +23,43 @@ int64_t& launch_counter() {
   return n;
 }
 
+// ---- profiling -------------------------------------------------------------------------------
+struct ProfRec {
+  int kind;
+  double flops, bytes;
+  cudaEvent_t a, b;
+};
+struct ProfState {
+  bool on = false;
+  std::vector<ProfRec*> recs;
+};
+static ProfState& prof() {
+  static thread_local ProfState p;
+  return p;
+}
+ProfScope::ProfScope(int kind_, double flops, double bytes, cudaStream_t st_) : kind(kind_), st(st_), rec(nullptr) {
+  if (!prof().on) return;
+  ProfRec* r = new ProfRec();
+  r->kind = kind;
+  r->flops = flops;
+  r->bytes = bytes;
+  cudaEventCreate(&r->a);
+  cudaEventCreate(&r->b);
+  cudaEventRecord(r->a, st);
+  rec = r;
+}
+ProfScope::~ProfScope() {
+  if (!rec) return;
+  ProfRec* r = (ProfRec*)rec;
+  cudaEventRecord(r->b, st);
+  prof().recs.push_back(r);
+}
+
 int launch_pack_level(const float* src, int n_views, int C, int H, int W, void* dst, int dtype, cudaStream_t st);
 int mlp_forward_tc_rows(const pnr_mlp& m, const float* zx, int SB, int NS, int P, float* out, void* ws,
                         size_t ws_bytes, cudaStream_t st);
 size_t mlp_tc_rows_workspace(const pnr_mlp& m, int SB, int NS, int P);
+int tc_check(cudaStream_t st);
 
 // pre-pool rows evaluated per internal chunk (bounds the scratch; rays are never split)
 static const long long kChunkRowsF32 = 1LL << 18;
@@ -143,6 +178,43 @@ int64_t pnr_launch_count(int reset) {
   if (reset) launch_counter() = 0;
   return v;
 }
+
+int pnr_profile_begin(void) {
+  for (ProfRec* r : prof().recs) {
+    cudaEventDestroy(r->a);
+    cudaEventDestroy(r->b);
+    delete r;
+  }
+  prof().recs.clear();
+  prof().on = true;
+  return PNR_OK;
+}
+
+int pnr_profile_end(double* ms, int64_t* launches, double* flops, double* bytes) {
+  prof().on = false;
+  for (int k = 0; k < PROF_KINDS; ++k) {
+    ms[k] = 0;
+    launches[k] = 0;
+    flops[k] = 0;
+    bytes[k] = 0;
+  }
+  PNR_CUDA(cudaDeviceSynchronize());
+  for (ProfRec* r : prof().recs) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r->a, r->b);
+    ms[r->kind] += t;
+    launches[r->kind] += 1;
+    flops[r->kind] += r->flops;
+    bytes[r->kind] += r->bytes;
+    cudaEventDestroy(r->a);
+    cudaEventDestroy(r->b);
+    delete r;
+  }
+  prof().recs.clear();
+  return PNR_OK;
+}
+
+int pnr_tc_check(pnr_stream stream) { return tc_check((cudaStream_t)stream); }
 
 int pnr_pack_level(const float* src, int n_views, int C, int H, int W, void* dst, int dst_dtype, pnr_stream stream) {
   PNR_CHECK_ARG(src && dst, "pack_level: NULL pointer");

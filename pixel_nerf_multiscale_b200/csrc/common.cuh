@@ -57,6 +57,17 @@ int64_t& launch_counter();
     if (_s != PNR_OK) return _s; \
   } while (0)
 
+// optional per-kernel timing (bench.py's roofline leg): CUDA events recorded on the launching
+// stream around the tracked kernels; thread-local, off by default.
+enum ProfKind { PROF_FEATURES = 0, PROF_PHASE_A = 1, PROF_PHASE_B = 2, PROF_KINDS = 3 };
+struct ProfScope {
+  int kind;
+  cudaStream_t st;
+  void* rec;
+  ProfScope(int kind, double flops, double bytes, cudaStream_t st);
+  ~ProfScope();
+};
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }

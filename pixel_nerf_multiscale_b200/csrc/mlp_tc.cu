@@ -1,10 +1,949 @@
-// placeholder -- replaced by the tcgen05 implementation
-#include "common.cuh"
+// Kernel (b), production path: ResnetFC (src/model/resnetfc.py:173-236) as a fused chain of
+// tcgen05 (UTCHMMA.2CTA) GEMMs with bf16 operands and fp32 accumulation in tensor memory.
+//
+// Design ("pair-64"): a cluster of 2 CTAs owns a tile of 128 (point,view) rows, 64 rows per CTA, and
+// issues cta_group::2 MMAs with M=128, N=256, K=16.  Per CTA:
+//   TMEM  512 columns = X (64 rows x 512 fp32 residual stream, accumulated IN PLACE by lin_z and
+//         fc_1 GEMMs, so the residual add costs nothing and never leaves fp32) + NET (fc_0 output)
+//   smem  S_x = relu(x) bf16 (64 KB) and H = relu(net) bf16 (64 KB) as K-major SWIZZLE_NONE UMMA
+//         operands, a 5 x 16 KB ring of weight chunks and a 2 x 8 KB ring of [latent|code] slices,
+//         all filled by 1-D bulk copies (UBLKCP) from pre-packed global images.
+//   warps 0 producer | 1 MMA issuer (leader CTA) / barrier relay (peer CTA) | 2 TMEM alloc |
+//         4-11 epilogue (TMEM -> +bias, relu -> bf16 operand panels; view mean-pool; lin_out head)
+// Phase A (rows = points x views): lin_in+lin_z[0], blocks 0..combine_layer-1, view mean-pool
+//         (util.combine_interleaved) -> pooled x (fp32) to global.
+// Phase B (rows = points): remaining blocks, lin_out, sigmoid/relu head (models.py.backup2:274-281).
+// The [latent|code] operand rows are produced by the bf16 variant of kernel (a) below
+// (128-bit gathers of the NHWC bf16 pyramid, written directly in UMMA panel order).
+#include "features.cuh"
+#include "tc_ptx.cuh"
+
 namespace pnr {
-size_t mlp_tc_packed_bytes(const pnr_mlp& m) { return 256; }
-int mlp_tc_pack(const pnr_mlp& m, void* dst, size_t dst_bytes, cudaStream_t st) { set_err("tc path not built"); return PNR_ERR_UNSUPPORTED; }
-size_t net_tc_workspace(const pnr_scene& sc, const pnr_mlp& m, int SB, long long P) { return 256; }
-int net_forward_tc(const pnr_scene& sc, const pnr_mlp& m, const float* xyz, const float* viewdirs, const float* rays, const float* z, int K, int SB, long long P, float* out, void* ws, size_t ws_bytes, cudaStream_t st) { set_err("tc path not built"); return PNR_ERR_UNSUPPORTED; }
-int mlp_forward_tc_rows(const pnr_mlp& m, const float* zx, int SB, int NS, int P, float* out, void* ws, size_t ws_bytes, cudaStream_t st) { set_err("tc path not built"); return PNR_ERR_UNSUPPORTED; }
-size_t mlp_tc_rows_workspace(const pnr_mlp& m, int SB, int NS, int P) { return 256; }
+using namespace ptx;
+
+// first barrier-timeout tag seen by any tensor-core kernel on this device (0 = none); read and
+// cleared by pnr_tc_check().  A protocol bug therefore fails loudly instead of hanging the GPU.
+__device__ int g_tc_err = 0;
+
+namespace tc {
+constexpr int DH = 512;                 // hidden width the tensor-core path is specialised for
+constexpr int ROWS = 64;                // rows per CTA
+constexpr int KS = 64;                  // K elements per slice
+constexpr int B_CHUNK = 128 * KS * 2;   // 16 KB: [8 k-groups][128 n-rows][8 bf16]
+constexpr int A_SLICE = ROWS * KS * 2;  // 8 KB : [8 k-groups][64 rows][8 bf16]
+constexpr int NB_ST = 5, NA_ST = 2;
+constexpr int OFF_SX = 0;
+constexpr int OFF_H = OFF_SX + ROWS * DH * 2;
+constexpr int OFF_BRING = OFF_H + ROWS * DH * 2;
+constexpr int OFF_ARING = OFF_BRING + NB_ST * B_CHUNK;
+constexpr int OFF_BARS = OFF_ARING + NA_ST * A_SLICE;
+constexpr int SMEM_BYTES = OFF_BARS + 512;
+constexpr int THREADS = 384;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+
+// barrier indices (uint64 each)
+constexpr int B_FULL = 0, B_EMPTY = B_FULL + NB_ST, A_FULL = B_EMPTY + NB_ST, A_EMPTY = A_FULL + NA_ST,
+              X_READY = A_EMPTY + NA_ST, NET_READY = X_READY + 1, SX_READY = NET_READY + 2, H_READY = SX_READY + 8,
+              XP_DONE = H_READY + 8, N_BARS = XP_DONE + 1;
+
+struct Params {
+  const uint8_t* w;                    // packed image base
+  uint32_t off_g1[PNR_MAX_BLOCKS];     // lin_in+lin_z[0] (b=0), lin_z[b] (b>0)
+  uint32_t off_g2[PNR_MAX_BLOCKS];     // fc_0
+  uint32_t off_g3[PNR_MAX_BLOCKS];     // fc_1
+  uint32_t off_biasA, off_biasB, off_bias0, off_lin_out;  // fp32 tables
+  int n_pre, n_post;                   // blocks before / after the view pool
+  int nks_z, nks_c;                    // K slices of the latent / code part of an input row
+  int ns, ppw;                         // views per point, points per 32-row group
+  long long P;                         // points
+  int tilesA, tilesB;
+  const uint8_t* zc;                   // [tileA][cta][slice][A_SLICE]
+  float* x3;                           // pooled residual stream, phase-B tile order
+  float* out;                          // (P,4)
+  int apply_head;
+  int* err;
+};
+}  // namespace tc
+using namespace tc;
+
+// ---------------------------------------------------------------------------------------------
+// row <-> point mapping of a phase-A tile: CTA c, row r: group rg=r/32, rr=r%32, point-in-group
+// pl=rr/ns, view v=rr%ns (rows with pl>=ppw are padding)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long tileA_point(int tile, int cta, int row, int ns, int ppw, int& v, bool& valid) {
+  int rg = row >> 5, rr = row & 31;
+  int pl = rr / ns;
+  v = rr - pl * ns;
+  valid = pl < ppw;
+  return ((long long)(tile * 2 + cta) * 2 + rg) * ppw + pl;
 }
+
+// =============================================================================================
+// weight packing
+// =============================================================================================
+struct PackJob {
+  const float* w;   // (512, K) row-major (nn.Linear weight)
+  int K;            // valid K columns of this source
+  int k_slices;     // 64-wide slices this source occupies
+  uint32_t dst_off; // byte offset of its first chunk
+};
+
+__global__ void pack_weights_kernel(PackJob job, uint8_t* __restrict__ dst) {
+  // one thread per 16-byte group: index = ((((s*2+nb)*2+c)*8+g)*128+i)
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)job.k_slices * 4 * 8 * 128;
+  if (idx >= total) return;
+  int i = (int)(idx & 127);
+  int g = (int)((idx >> 7) & 7);
+  int c = (int)((idx >> 10) & 1);
+  int nb = (int)((idx >> 11) & 1);
+  int s = (int)(idx >> 12);
+  int n = nb * 256 + c * 128 + i;
+  int k0 = s * 64 + g * 8;
+  uint32_t v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float lo = (k0 + 2 * e < job.K) ? job.w[(size_t)n * job.K + k0 + 2 * e] : 0.f;
+    float hi = (k0 + 2 * e + 1 < job.K) ? job.w[(size_t)n * job.K + k0 + 2 * e + 1] : 0.f;
+    v[e] = pack_bf16x2(lo, hi);
+  }
+  *reinterpret_cast<uint4*>(dst + job.dst_off + idx * 16) = make_uint4(v[0], v[1], v[2], v[3]);
+}
+
+__global__ void pack_bias_kernel(const float* a, const float* b, const float* c, const float* prev, float* dst, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = prev ? prev[i] : 0.f;
+  if (a) v += a[i];
+  if (b) v += b[i];
+  if (c) v += c[i];
+  dst[i] = v;
+}
+
+struct Layout {
+  uint32_t off_g1[PNR_MAX_BLOCKS], off_g2[PNR_MAX_BLOCKS], off_g3[PNR_MAX_BLOCKS];
+  uint32_t off_biasA, off_biasB, off_bias0, off_lin_out;
+  int n_pre, n_post, nks_z, nks_c;
+  size_t total;
+};
+
+static int tc_supported(const pnr_mlp& m) {
+  PNR_UNSUPPORTED(m.d_hidden != DH, "tensor-core MLP is specialised for d_hidden=512 (got %d); use precision fp32", m.d_hidden);
+  PNR_UNSUPPORTED(m.d_latent <= 0 || m.d_latent % 64 != 0, "tensor-core MLP needs d_latent %% 64 == 0 (got %d)", m.d_latent);
+  PNR_UNSUPPORTED(m.d_in <= 0 || m.d_in > 128, "tensor-core MLP needs 0 < d_in <= 128 (got %d)", m.d_in);
+  PNR_UNSUPPORTED(m.d_out != 4, "tensor-core MLP needs d_out == 4");
+  PNR_UNSUPPORTED(m.n_lin_z != (m.combine_layer < m.n_blocks ? m.combine_layer : m.n_blocks),
+                  "unexpected number of lin_z layers");
+  PNR_UNSUPPORTED(m.n_lin_z < 1, "tensor-core MLP needs at least one latent injection (combine_layer >= 1)");
+  return PNR_OK;
+}
+
+static Layout make_layout(const pnr_mlp& m) {
+  Layout L;
+  memset(&L, 0, sizeof(L));
+  L.n_pre = m.combine_layer < m.n_blocks ? m.combine_layer : m.n_blocks;
+  L.n_post = m.n_blocks - L.n_pre;
+  L.nks_z = m.d_latent / 64;
+  L.nks_c = (m.d_in + 63) / 64;
+  size_t off = 0;
+  auto group = [&](int slices) {
+    uint32_t o = (uint32_t)off;
+    off += (size_t)slices * 4 * B_CHUNK;
+    return o;
+  };
+  for (int b = 0; b < m.n_blocks; ++b) {
+    if (b < L.n_pre) L.off_g1[b] = group(b == 0 ? L.nks_z + L.nks_c : L.nks_z);
+    L.off_g2[b] = group(DH / 64);
+    L.off_g3[b] = group(DH / 64);
+  }
+  L.off_biasA = (uint32_t)off;  off += (size_t)(L.n_pre + 1) * DH * 4;
+  L.off_biasB = (uint32_t)off;  off += (size_t)(L.n_post + 1) * DH * 4;
+  L.off_bias0 = (uint32_t)off;  off += (size_t)m.n_blocks * DH * 4;
+  L.off_lin_out = (uint32_t)off; off += (size_t)(4 * DH + 4) * 4;
+  L.total = align_up(off, 256);
+  return L;
+}
+
+size_t mlp_tc_packed_bytes(const pnr_mlp& m) {
+  if (tc_supported(m) != PNR_OK) return 256;
+  return make_layout(m).total;
+}
+
+int mlp_tc_pack(const pnr_mlp& m, void* dst, size_t dst_bytes, cudaStream_t st) {
+  PNR_TRY(tc_supported(m));
+  Layout L = make_layout(m);
+  PNR_CHECK_ARG(dst_bytes >= L.total, "mlp_pack: destination too small (%zu < %zu)", dst_bytes, L.total);
+  PNR_CHECK_ARG(((uintptr_t)dst & 15) == 0, "mlp_pack: destination must be 16-byte aligned");
+  uint8_t* d = (uint8_t*)dst;
+  auto pack = [&](const float* w, int K, int slices, uint32_t off) -> int {
+    PackJob j{w, K, slices, off};
+    long long total = (long long)slices * 4 * 8 * 128;
+    pack_weights_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(j, d);
+    PNR_LAUNCHED();
+    return PNR_OK;
+  };
+  for (int b = 0; b < m.n_blocks; ++b) {
+    if (b < L.n_pre) {
+      PNR_TRY(pack(m.lin_z_w[b], m.d_latent, L.nks_z, L.off_g1[b]));
+      if (b == 0) PNR_TRY(pack(m.lin_in_w, m.d_in, L.nks_c, L.off_g1[0] + (uint32_t)L.nks_z * 4 * B_CHUNK));
+    }
+    PNR_TRY(pack(m.fc0_w[b], DH, DH / 64, L.off_g2[b]));
+    PNR_TRY(pack(m.fc1_w[b], DH, DH / 64, L.off_g3[b]));
+  }
+  // bias tables.  biasA[b]: constant to add to the TMEM residual when it is read before block b of
+  // phase A (the GEMMs accumulate without biases); biasA[n_pre] is the pooled output's constant.
+  float* biasA = (float*)(d + L.off_biasA);
+  float* biasB = (float*)(d + L.off_biasB);
+  float* bias0 = (float*)(d + L.off_bias0);
+  auto bias = [&](const float* a, const float* b, const float* c, const float* prev, float* out) -> int {
+    pack_bias_kernel<<<2, 256, 0, st>>>(a, b, c, prev, out, DH);
+    PNR_LAUNCHED();
+    return PNR_OK;
+  };
+  PNR_TRY(bias(m.lin_in_b, m.lin_z_b[0], nullptr, nullptr, biasA));
+  for (int b = 1; b <= L.n_pre; ++b)
+    PNR_TRY(bias(m.fc1_b[b - 1], b < L.n_pre ? m.lin_z_b[b] : nullptr, nullptr, biasA + (size_t)(b - 1) * DH,
+                 biasA + (size_t)b * DH));
+  PNR_TRY(bias(nullptr, nullptr, nullptr, nullptr, biasB));  // pooled x is stored exactly
+  for (int j = 1; j <= L.n_post; ++j)
+    PNR_TRY(bias(m.fc1_b[L.n_pre + j - 1], nullptr, nullptr, biasB + (size_t)(j - 1) * DH, biasB + (size_t)j * DH));
+  for (int b = 0; b < m.n_blocks; ++b) PNR_TRY(bias(m.fc0_b[b], nullptr, nullptr, nullptr, bias0 + (size_t)b * DH));
+  PNR_CUDA(cudaMemcpyAsync(d + L.off_lin_out, m.lin_out_w, (size_t)4 * DH * 4, cudaMemcpyDeviceToDevice, st));
+  PNR_CUDA(cudaMemcpyAsync(d + L.off_lin_out + (size_t)4 * DH * 4, m.lin_out_b, 16, cudaMemcpyDeviceToDevice, st));
+  return PNR_OK;
+}
+
+// =============================================================================================
+// kernel (a), bf16 operand variant: one warp per tile row; writes [latent | code] straight into the
+// phase-A operand image  zc[tile][cta][k-group][row][8 bf16]
+// =============================================================================================
+__device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+point_features_bf16_kernel(const pnr_scene sc, const float* __restrict__ xyz, const float* __restrict__ viewdirs,
+                           const float* __restrict__ rays, const float* __restrict__ z, int K, long long P, int ppw,
+                           int tilesA, int nks_z, int nks_c, uint8_t* __restrict__ zc) {
+  const int lane = threadIdx.x & 31;
+  const long long wrow = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wrow >= (long long)tilesA * 128) return;
+  const int tile = (int)(wrow >> 7), cta = (int)((wrow >> 6) & 1), row = (int)(wrow & 63);
+  int v;
+  bool valid;
+  long long gp = tileA_point(tile, cta, row, sc.ns, ppw, v, valid);
+  valid = valid && gp < P;
+  const int nsl = nks_z + nks_c;
+  uint8_t* base = zc + ((size_t)(tile * 2 + cta) * nsl) * A_SLICE + (size_t)row * 16;  // + kgroup*1024
+  if (!valid) {
+    for (int g = lane; g < nsl * 8; g += 32) *reinterpret_cast<uint4*>(base + (size_t)g * 1024) = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  float X[3], D[3];
+  load_point(xyz, viewdirs, rays, z, K, gp, X, D);
+  PointCam pc;
+  camera_project(sc.cams + v * 16, X, D, pc);
+  for (int l = 0; l < sc.n_levels; ++l) {
+    const int C = sc.C[l], H = sc.H[l], W = sc.W[l];
+    Taps t = make_taps(pc.u, pc.v, H, W, sc.kx[l], sc.ky[l]);
+    const __nv_bfloat16* f = (const __nv_bfloat16*)sc.level[l] + (size_t)v * H * W * C;
+    for (int g = lane; g < (C >> 3); g += 32) {
+      // 4 x 128-bit loads: 8 consecutive channels of each tap (NHWC -> a warp reads 512 B per tap)
+      uint4 q00 = __ldg(reinterpret_cast<const uint4*>(f + (size_t)t.o00 * C) + g);
+      uint4 q01 = __ldg(reinterpret_cast<const uint4*>(f + (size_t)t.o01 * C) + g);
+      uint4 q10 = __ldg(reinterpret_cast<const uint4*>(f + (size_t)t.o10 * C) + g);
+      uint4 q11 = __ldg(reinterpret_cast<const uint4*>(f + (size_t)t.o11 * C) + g);
+      float a[8], b[8], c[8], d[8];
+      bf16x8_to_float(q00, a);
+      bf16x8_to_float(q01, b);
+      bf16x8_to_float(q10, c);
+      bf16x8_to_float(q11, d);
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float lo = a[2 * e] * t.w00 + b[2 * e] * t.w01 + c[2 * e] * t.w10 + d[2 * e] * t.w11;
+        float hi = a[2 * e + 1] * t.w00 + b[2 * e + 1] * t.w01 + c[2 * e + 1] * t.w10 + d[2 * e + 1] * t.w11;
+        o[e] = pack_bf16x2(lo, hi);
+      }
+      int kg = (sc.ch_off[l] >> 3) + g;
+      *reinterpret_cast<uint4*>(base + (size_t)kg * 1024) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  // zero padding of the latent part (d_latent is a multiple of 64 on this path) is not needed;
+  // code part: nks_c slices, entries >= d_in are zero
+  for (int g = lane; g < nks_c * 8; g += 32) {
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int j = g * 8 + 2 * e;
+      float lo = j < sc.d_in ? code_entry(sc, pc, j) : 0.f;
+      float hi = j + 1 < sc.d_in ? code_entry(sc, pc, j + 1) : 0.f;
+      o[e] = pack_bf16x2(lo, hi);
+    }
+    *reinterpret_cast<uint4*>(base + (size_t)(nks_z * 8 + g) * 1024) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// fp32 rows in reference order (sb, ns, p) -> operand image (used by pnr_mlp_forward in bf16 mode)
+__global__ void __launch_bounds__(256)
+rows_to_operand_kernel(const float* __restrict__ zx, int d_latent, int d_in, int SB, int NS, long long Pper, int ppw,
+                       int tilesA, int nks_z, int nks_c, uint8_t* __restrict__ zc) {
+  const int lane = threadIdx.x & 31;
+  const long long wrow = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wrow >= (long long)tilesA * 128) return;
+  const int tile = (int)(wrow >> 7), cta = (int)((wrow >> 6) & 1), row = (int)(wrow & 63);
+  int v;
+  bool valid;
+  long long gp = tileA_point(tile, cta, row, NS, ppw, v, valid);
+  valid = valid && gp < (long long)SB * Pper;
+  const int nsl = nks_z + nks_c;
+  uint8_t* base = zc + ((size_t)(tile * 2 + cta) * nsl) * A_SLICE + (size_t)row * 16;
+  const int width = d_latent + d_in;
+  const float* src = nullptr;
+  if (valid) {
+    long long sb = gp / Pper, p = gp - sb * Pper;
+    src = zx + ((sb * NS + v) * Pper + p) * width;
+  }
+  for (int g = lane; g < nsl * 8; g += 32) {
+    uint32_t o[4] = {0, 0, 0, 0};
+    if (valid) {
+      bool is_code = g >= nks_z * 8;
+      int k0 = is_code ? (g - nks_z * 8) * 8 : g * 8;
+      int lim = is_code ? d_in : d_latent;
+      const float* s = src + (is_code ? d_latent : 0);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float lo = (k0 + 2 * e < lim) ? s[k0 + 2 * e] : 0.f;
+        float hi = (k0 + 2 * e + 1 < lim) ? s[k0 + 2 * e + 1] : 0.f;
+        o[e] = pack_bf16x2(lo, hi);
+      }
+    }
+    *reinterpret_cast<uint4*>(base + (size_t)g * 1024) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// =============================================================================================
+// the fused MLP kernels
+// =============================================================================================
+struct Ring {
+  uint32_t full, empty;  // smem addresses of barrier arrays
+  int n, idx;
+  uint32_t phase;
+  __device__ __forceinline__ void init(uint32_t f, uint32_t e, int n_) { full = f; empty = e; n = n_; idx = 0; phase = 0; }
+  __device__ __forceinline__ void advance() { if (++idx == n) { idx = 0; phase ^= 1; } }
+  __device__ __forceinline__ uint32_t full_bar() const { return full + idx * 8; }
+  __device__ __forceinline__ uint32_t empty_bar() const { return empty + idx * 8; }
+};
+
+struct Ctx {
+  uint32_t smem;   // shared::cta base address
+  uint32_t bars;   // address of barrier 0
+  uint32_t tmem;
+  uint32_t rank;
+  int* err;
+  __device__ __forceinline__ uint32_t bar(int i) const { return bars + i * 8; }
+};
+
+// ---- producer side helpers ----------------------------------------------------------------------
+__device__ __forceinline__ void load_b(const Ctx& cx, Ring& rb, const uint8_t* src) {
+  mbar_wait(rb.empty_bar(), rb.phase ^ 1, cx.err, 201);
+  mbar_expect_tx(rb.full_bar(), B_CHUNK);
+  bulk_g2s(cx.smem + OFF_BRING + rb.idx * B_CHUNK, src, B_CHUNK, rb.full_bar());
+  rb.advance();
+}
+__device__ __forceinline__ void load_a(const Ctx& cx, Ring& ra, const uint8_t* src) {
+  mbar_wait(ra.empty_bar(), ra.phase ^ 1, cx.err, 202);
+  mbar_expect_tx(ra.full_bar(), A_SLICE);
+  bulk_g2s(cx.smem + OFF_ARING + ra.idx * A_SLICE, src, A_SLICE, ra.full_bar());
+  ra.advance();
+}
+// weight chunk (slice s, column block nb) of a GEMM group for this CTA
+__device__ __forceinline__ const uint8_t* wchunk(const Params& p, uint32_t off, int s, int nb, uint32_t rank) {
+  return p.w + off + (size_t)((s * 2 + nb) * 2 + rank) * B_CHUNK;
+}
+
+// ---- MMA side helpers -----------------------------------------------------------------------------
+// Leader: waits for both CTAs' copies of the ring slot, issues 4 MMAs (K=64), releases the slot.
+// Peer:   waits for its own copy and relays the arrival to the leader's barrier.
+__device__ __forceinline__ void mma_step_b(const Ctx& cx, Ring& rb, uint32_t a_addr, uint32_t d_col, bool first) {
+  mbar_wait(rb.full_bar(), rb.phase, cx.err, 301);
+  if (cx.rank == 0) {
+    tc_fence_after();
+    const uint32_t idesc = idesc_bf16_f32(128, 256);
+    const uint32_t b_addr = cx.smem + OFF_BRING + rb.idx * B_CHUNK;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint64_t da = smem_desc(a_addr + kk * 2 * (ROWS * 16), ROWS * 16, 128);
+      uint64_t db = smem_desc(b_addr + kk * 2 * (128 * 16), 128 * 16, 128);
+      mma_bf16<2>(cx.tmem + d_col, da, db, idesc, (first && kk == 0) ? 0u : 1u);
+    }
+    mma_commit<2>(rb.empty_bar(), 0x3);
+  } else {
+    mbar_arrive_cluster(rb.full_bar(), 0);
+  }
+  rb.advance();
+}
+__device__ __forceinline__ void a_wait(const Ctx& cx, Ring& ra) {
+  mbar_wait(ra.full_bar(), ra.phase, cx.err, 302);
+  if (cx.rank != 0) mbar_arrive_cluster(ra.full_bar(), 0);
+}
+__device__ __forceinline__ void a_release(const Ctx& cx, Ring& ra) {
+  if (cx.rank == 0) mma_commit<2>(ra.empty_bar(), 0x3);
+  ra.advance();
+}
+__device__ __forceinline__ void signal(const Ctx& cx, int bar_idx) {
+  if (cx.rank == 0) mma_commit<2>(cx.bar(bar_idx), 0x3);
+}
+
+// x[:, all 512] (+)= A_ring @ W^T over `nks` slices (k-outer).  first_acc0: overwrite on slice 0.
+__device__ __forceinline__ void gemm_from_ring(const Ctx& cx, Ring& ra, Ring& rb, int nks, uint32_t xcol, bool overwrite) {
+  for (int s = 0; s < nks; ++s) {
+    a_wait(cx, ra);
+    uint32_t a_addr = cx.smem + OFF_ARING + ra.idx * A_SLICE;
+    for (int nb = 0; nb < 2; ++nb) mma_step_b(cx, rb, a_addr, xcol + nb * 128, overwrite && s == 0);
+    a_release(cx, ra);
+  }
+}
+// NET = S_x @ W0^T, n-outer; waits for operand slices as the epilogue publishes them
+__device__ __forceinline__ void gemm_fc0(const Ctx& cx, Ring& rb, uint32_t netcol, uint32_t sx_phase) {
+  for (int nb = 0; nb < 2; ++nb) {
+    for (int s = 0; s < DH / KS; ++s) {
+      if (nb == 0 && cx.rank == 0) mbar_wait(cx.bar(SX_READY + s), sx_phase, cx.err, 310 + s);
+      mma_step_b(cx, rb, cx.smem + OFF_SX + s * A_SLICE, netcol + nb * 128, s == 0);
+    }
+    signal(cx, NET_READY + nb);
+  }
+}
+// X += H @ W1^T, k-outer
+__device__ __forceinline__ void gemm_fc1(const Ctx& cx, Ring& rb, uint32_t xcol, uint32_t h_phase) {
+  for (int s = 0; s < DH / KS; ++s) {
+    if (cx.rank == 0) mbar_wait(cx.bar(H_READY + s), h_phase, cx.err, 320 + s);
+    for (int nb = 0; nb < 2; ++nb) mma_step_b(cx, rb, cx.smem + OFF_H + s * A_SLICE, xcol + nb * 128, false);
+  }
+}
+
+// ---- epilogue helpers -------------------------------------------------------------------------------
+struct Epi {
+  int q, cs, h, row, lane;  // TMEM quadrant, column split, column half of the 2x2 layout, tile row
+  uint32_t lane_addr;       // (q*32) << 16
+};
+__device__ __forceinline__ Epi make_epi(int warp, int lane) {
+  Epi e;
+  e.q = warp & 3;
+  e.cs = (warp - 4) >> 2;
+  e.h = e.q >> 1;
+  e.row = (e.q & 1) * 32 + lane;
+  e.lane = lane;
+  e.lane_addr = (uint32_t)(e.q * 32) << 16;
+  return e;
+}
+// feature index of column i of the 32-column group (nb, half) held by this thread
+__device__ __forceinline__ int feat0(const Epi& e, int nb, int half) { return nb * 256 + e.h * 128 + e.cs * 64 + half * 32; }
+
+// TMEM (64 columns of block nb) -> relu(v + bias) -> bf16 operand panels in `dst_off`; publishes slice
+__device__ __forceinline__ void epi_to_operand(const Ctx& cx, const Epi& e, uint32_t col, int nb, const float* __restrict__ bias,
+                                               uint32_t dst_off, int ready_bar0) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t r[32];
+    tmem_ld32(cx.tmem + e.lane_addr + col + nb * 128 + e.cs * 64 + half * 32, r);
+    tmem_ld_wait();
+    const int f0 = feat0(e, nb, half);
+    const float4* b4 = reinterpret_cast<const float4*>(bias + f0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // 8 features -> one 16-byte k-group entry
+      float4 ba = __ldg(b4 + 2 * j), bb = __ldg(b4 + 2 * j + 1);
+      float v0 = fmaxf(__uint_as_float(r[8 * j + 0]) + ba.x, 0.f), v1 = fmaxf(__uint_as_float(r[8 * j + 1]) + ba.y, 0.f);
+      float v2 = fmaxf(__uint_as_float(r[8 * j + 2]) + ba.z, 0.f), v3 = fmaxf(__uint_as_float(r[8 * j + 3]) + ba.w, 0.f);
+      float v4 = fmaxf(__uint_as_float(r[8 * j + 4]) + bb.x, 0.f), v5 = fmaxf(__uint_as_float(r[8 * j + 5]) + bb.y, 0.f);
+      float v6 = fmaxf(__uint_as_float(r[8 * j + 6]) + bb.z, 0.f), v7 = fmaxf(__uint_as_float(r[8 * j + 7]) + bb.w, 0.f);
+      uint32_t kg = (uint32_t)(f0 >> 3) + j;
+      uint32_t addr = cx.smem + dst_off + kg * (ROWS * 16) + e.row * 16;
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(v0, v1)),
+                   "r"(pack_bf16x2(v2, v3)), "r"(pack_bf16x2(v4, v5)), "r"(pack_bf16x2(v6, v7))
+                   : "memory");
+    }
+  }
+  tc_fence_before();
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (e.lane == 0) mbar_arrive_cluster(cx.bar(ready_bar0 + nb * 4 + e.h * 2 + e.cs), 0);
+}
+
+__device__ __forceinline__ void setup_barriers(const Ctx& cx) {
+  const uint32_t full_cnt = cx.rank == 0 ? 2 : 1;
+  for (int i = 0; i < NB_ST; ++i) { mbar_init(cx.bar(B_FULL + i), full_cnt); mbar_init(cx.bar(B_EMPTY + i), 1); }
+  for (int i = 0; i < NA_ST; ++i) { mbar_init(cx.bar(A_FULL + i), full_cnt); mbar_init(cx.bar(A_EMPTY + i), 1); }
+  mbar_init(cx.bar(X_READY), 1);
+  mbar_init(cx.bar(NET_READY), 1);
+  mbar_init(cx.bar(NET_READY + 1), 1);
+  for (int i = 0; i < 8; ++i) { mbar_init(cx.bar(SX_READY + i), 4); mbar_init(cx.bar(H_READY + i), 4); }
+  mbar_init(cx.bar(XP_DONE), 16);
+  fence_mbar_init();
+}
+
+// =============================================================================================
+// Phase A
+// =============================================================================================
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phaseA_kernel(const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Ctx cx;
+  cx.smem = smem_u32(smem_raw);
+  cx.bars = cx.smem + OFF_BARS;
+  cx.rank = cluster_ctarank();
+  cx.err = &g_tc_err;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + OFF_BARS + N_BARS * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) setup_barriers(cx);
+  if (warp == 2) {
+    tmem_alloc<2>(smem_u32(tmem_slot), 512);
+    tmem_relinquish<2>();
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  cx.tmem = *tmem_slot;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int nsl = p.nks_z + p.nks_c;
+
+  if (warp == 0) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      Ring ra, rb;
+      ra.init(cx.bar(A_FULL), cx.bar(A_EMPTY), NA_ST);
+      rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST);
+      for (int tile = pair; tile < p.tilesA; tile += npairs) {
+        const uint8_t* zt = p.zc + ((size_t)(tile * 2 + cx.rank) * nsl) * A_SLICE;
+        for (int s = 0; s < nsl; ++s) {
+          load_a(cx, ra, zt + (size_t)s * A_SLICE);
+          for (int nb = 0; nb < 2; ++nb) load_b(cx, rb, wchunk(p, p.off_g1[0], s, nb, cx.rank));
+        }
+        for (int b = 0; b < p.n_pre; ++b) {
+          for (int nb = 0; nb < 2; ++nb)
+            for (int s = 0; s < DH / KS; ++s) load_b(cx, rb, wchunk(p, p.off_g2[b], s, nb, cx.rank));
+          if (b + 1 < p.n_pre)
+            for (int s = 0; s < p.nks_z; ++s) {
+              load_a(cx, ra, zt + (size_t)s * A_SLICE);
+              for (int nb = 0; nb < 2; ++nb) load_b(cx, rb, wchunk(p, p.off_g1[b + 1], s, nb, cx.rank));
+            }
+          for (int s = 0; s < DH / KS; ++s)
+            for (int nb = 0; nb < 2; ++nb) load_b(cx, rb, wchunk(p, p.off_g3[b], s, nb, cx.rank));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader) / relay (peer) =====================
+    if (lane == 0) {
+      Ring ra, rb;
+      ra.init(cx.bar(A_FULL), cx.bar(A_EMPTY), NA_ST);
+      rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST);
+      uint32_t use = 0;  // (tile-local block counter) parity source for SX/H barriers
+      uint32_t it = 0;
+      for (int tile = pair; tile < p.tilesA; tile += npairs, ++it) {
+        const uint32_t xcol = (it & 1) ? 256u : 0u, netcol = 256u - xcol;
+        gemm_from_ring(cx, ra, rb, nsl, xcol, true);
+        signal(cx, X_READY);
+        for (int b = 0; b < p.n_pre; ++b, ++use) {
+          if (b == 0 && it > 0 && cx.rank == 0) mbar_wait(cx.bar(XP_DONE), (it - 1) & 1, cx.err, 330);
+          gemm_fc0(cx, rb, netcol, use & 1);
+          if (b + 1 < p.n_pre) gemm_from_ring(cx, ra, rb, p.nks_z, xcol, false);
+          gemm_fc1(cx, rb, xcol, use & 1);
+          signal(cx, X_READY);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const Epi e = make_epi(warp, lane);
+    const float* biasA = reinterpret_cast<const float*>(p.w + p.off_biasA);
+    const float* bias0 = reinterpret_cast<const float*>(p.w + p.off_bias0);
+    uint32_t xph = 0, nph = 0, it = 0;
+    for (int tile = pair; tile < p.tilesA; tile += npairs, ++it) {
+      const uint32_t xcol = (it & 1) ? 256u : 0u, netcol = 256u - xcol;
+      for (int b = 0; b < p.n_pre; ++b) {
+        mbar_wait(cx.bar(X_READY), xph, cx.err, 401);
+        xph ^= 1;
+        tc_fence_after();
+        for (int nb = 0; nb < 2; ++nb) epi_to_operand(cx, e, xcol, nb, biasA + (size_t)b * DH, OFF_SX, SX_READY);
+        for (int nb = 0; nb < 2; ++nb) {
+          mbar_wait(cx.bar(NET_READY + nb), nph, cx.err, 402 + nb);
+          tc_fence_after();
+          epi_to_operand(cx, e, netcol, nb, bias0 + (size_t)b * DH, OFF_H, H_READY);
+        }
+        nph ^= 1;
+      }
+      // ---- view mean-pool of the residual stream -> pooled x (fp32) in phase-B tile order ----
+      mbar_wait(cx.bar(X_READY), xph, cx.err, 405);
+      xph ^= 1;
+      tc_fence_after();
+      int v;
+      bool valid;
+      long long gp = tileA_point(tile, (int)cx.rank, e.row, p.ns, p.ppw, v, valid);
+      valid = valid && v == 0 && gp < p.P;
+      const float* bP = biasA + (size_t)p.n_pre * DH;
+      const float inv = (float)p.ns;
+      for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32];
+          tmem_ld32(cx.tmem + e.lane_addr + xcol + nb * 128 + e.cs * 64 + half * 32, r);
+          tmem_ld_wait();
+          const int f0 = feat0(e, nb, half);
+          float acc[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x = __uint_as_float(r[i]);
+            float s = x;
+            for (int k = 1; k < p.ns; ++k) s += __shfl_down_sync(0xffffffffu, x, k);
+            acc[i] = s / inv + __ldg(bP + f0 + i);
+          }
+          if (valid) {
+            const long long tb = gp >> 7;
+            const int cb = (int)((gp >> 6) & 1), rb_ = (int)(gp & 63);
+            // x3[tileB][ctaB][nb][h][jq (32)][row (64)][4]
+            float4* dst = reinterpret_cast<float4*>(p.x3) +
+                          ((((tb * 2 + cb) * 2 + nb) * 2 + e.h) * 32 + (e.cs * 16 + half * 8)) * 64 + rb_;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[(size_t)j * 64] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+          }
+        }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(cx.bar(XP_DONE), 0);
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 2) tmem_dealloc<2>(cx.tmem, 512);
+}
+
+// =============================================================================================
+// Phase B
+// =============================================================================================
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phaseB_kernel(const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Ctx cx;
+  cx.smem = smem_u32(smem_raw);
+  cx.bars = cx.smem + OFF_BARS;
+  cx.rank = cluster_ctarank();
+  cx.err = &g_tc_err;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + OFF_BARS + N_BARS * 8);
+  float* s_wout = reinterpret_cast<float*>(smem_raw + OFF_ARING);          // [4][512] + [4]
+  float* s_part = s_wout + 4 * DH + 4;                                    // [4 outputs][4 parts][64 rows]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) setup_barriers(cx);
+  if (warp == 2) {
+    tmem_alloc<2>(smem_u32(tmem_slot), 512);
+    tmem_relinquish<2>();
+  }
+  {
+    const float* wo = reinterpret_cast<const float*>(p.w + p.off_lin_out);
+    for (int i = threadIdx.x; i < 4 * DH + 4; i += blockDim.x) s_wout[i] = wo[i];
+  }
+  __syncthreads();
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  cx.tmem = *tmem_slot;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const uint32_t xcol = 0, netcol = 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      Ring rb;
+      rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST);
+      for (int tile = pair; tile < p.tilesB; tile += npairs)
+        for (int j = 0; j < p.n_post; ++j) {
+          const int b = p.n_pre + j;
+          for (int nb = 0; nb < 2; ++nb)
+            for (int s = 0; s < DH / KS; ++s) load_b(cx, rb, wchunk(p, p.off_g2[b], s, nb, cx.rank));
+          for (int s = 0; s < DH / KS; ++s)
+            for (int nb = 0; nb < 2; ++nb) load_b(cx, rb, wchunk(p, p.off_g3[b], s, nb, cx.rank));
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      Ring rb;
+      rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST);
+      uint32_t use = 0;
+      for (int tile = pair; tile < p.tilesB; tile += npairs)
+        for (int j = 0; j < p.n_post; ++j, ++use) {
+          gemm_fc0(cx, rb, netcol, use & 1);
+          gemm_fc1(cx, rb, xcol, use & 1);
+          signal(cx, X_READY);
+        }
+    }
+  } else if (warp >= 4) {
+    const Epi e = make_epi(warp, lane);
+    const float* biasB = reinterpret_cast<const float*>(p.w + p.off_biasB);
+    const float* bias0 = reinterpret_cast<const float*>(p.w + p.off_bias0);
+    uint32_t xph = 0, nph = 0;
+    for (int tile = pair; tile < p.tilesB; tile += npairs) {
+      const long long gp = (long long)tile * 128 + cx.rank * 64 + e.row;
+      const bool valid = gp < p.P;
+      // ---- load pooled x: fp32 -> TMEM residual, relu -> bf16 operand ----
+      for (int nb = 0; nb < 2; ++nb) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const float4* src = reinterpret_cast<const float4*>(p.x3) +
+                              (((((long long)tile * 2 + cx.rank) * 2 + nb) * 2 + e.h) * 32 + (e.cs * 16 + half * 8)) * 64 + e.row;
+          uint32_t r[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 t = valid ? __ldg(src + (size_t)j * 64) : make_float4(0.f, 0.f, 0.f, 0.f);
+            r[4 * j] = __float_as_uint(t.x);
+            r[4 * j + 1] = __float_as_uint(t.y);
+            r[4 * j + 2] = __float_as_uint(t.z);
+            r[4 * j + 3] = __float_as_uint(t.w);
+          }
+          tmem_st32(cx.tmem + e.lane_addr + xcol + nb * 128 + e.cs * 64 + half * 32, r);
+          const int f0 = feat0(e, nb, half);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t kg = (uint32_t)(f0 >> 3) + j;
+            uint32_t addr = cx.smem + OFF_SX + kg * (ROWS * 16) + e.row * 16;
+            auto rl = [&](int i) { return fmaxf(__uint_as_float(r[8 * j + i]), 0.f); };
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(rl(0), rl(1))),
+                         "r"(pack_bf16x2(rl(2), rl(3))), "r"(pack_bf16x2(rl(4), rl(5))), "r"(pack_bf16x2(rl(6), rl(7)))
+                         : "memory");
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (p.n_post > 0 && lane == 0) mbar_arrive_cluster(cx.bar(SX_READY + nb * 4 + e.h * 2 + e.cs), 0);
+      }
+      for (int j = 0; j < p.n_post; ++j) {
+        const int b = p.n_pre + j;
+        for (int nb = 0; nb < 2; ++nb) {
+          mbar_wait(cx.bar(NET_READY + nb), nph, cx.err, 502 + nb);
+          tc_fence_after();
+          epi_to_operand(cx, e, netcol, nb, bias0 + (size_t)b * DH, OFF_H, H_READY);
+        }
+        nph ^= 1;
+        mbar_wait(cx.bar(X_READY), xph, cx.err, 501);
+        xph ^= 1;
+        tc_fence_after();
+        if (j + 1 < p.n_post)
+          for (int nb = 0; nb < 2; ++nb) epi_to_operand(cx, e, xcol, nb, biasB + (size_t)(j + 1) * DH, OFF_SX, SX_READY);
+      }
+      // ---- lin_out(relu(x)) + head ----
+      const float* bO = biasB + (size_t)p.n_post * DH;
+      float part[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32];
+          tmem_ld32(cx.tmem + e.lane_addr + xcol + nb * 128 + e.cs * 64 + half * 32, r);
+          tmem_ld_wait();
+          const int f0 = feat0(e, nb, half);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x = fmaxf(__uint_as_float(r[i]) + __ldg(bO + f0 + i), 0.f);
+#pragma unroll
+            for (int o = 0; o < 4; ++o) part[o] = fmaf(x, s_wout[o * DH + f0 + i], part[o]);
+          }
+        }
+      tc_fence_before();
+#pragma unroll
+      for (int o = 0; o < 4; ++o) s_part[(o * 4 + e.h * 2 + e.cs) * 64 + e.row] = part[o];
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp < 6) {  // 64 threads: one per row
+        const int row = (warp - 4) * 32 + lane;
+        const long long g = (long long)tile * 128 + cx.rank * 64 + row;
+        if (g < p.P) {
+          float o4[4];
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            float s = s_wout[4 * DH + o];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s += s_part[(o * 4 + q) * 64 + row];
+            if (p.apply_head) s = (o < 3) ? 1.f / (1.f + __expf(-s)) : fmaxf(s, 0.f);
+            o4[o] = s;
+          }
+          reinterpret_cast<float4*>(p.out)[g] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 2) tmem_dealloc<2>(cx.tmem, 512);
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+struct Plan {
+  int ppw, ptile, tilesA, tilesB, nsl;
+  uint8_t* zc;
+  float* x3;
+  int* err;
+  size_t total;
+};
+
+static Plan make_plan(const Layout& L, int ns, long long P, void* ws, size_t ws_bytes) {
+  Plan pl;
+  pl.ppw = 32 / ns;
+  pl.ptile = 4 * pl.ppw;
+  pl.tilesA = (int)ceil_div_ll(P, pl.ptile);
+  pl.tilesB = (int)ceil_div_ll(P, 128);
+  pl.nsl = L.nks_z + L.nks_c;
+  Arena a(ws, ws_bytes);
+  pl.zc = a.take<uint8_t>((size_t)pl.tilesA * 2 * pl.nsl * A_SLICE);
+  pl.x3 = a.take<float>((size_t)pl.tilesB * 128 * DH);
+  pl.err = a.take<int>(4);
+  pl.total = a.off + 256;
+  return pl;
+}
+
+static int launch_cluster(void (*kern)(const Params), int pairs, const Params& p, cudaStream_t st) {
+  PNR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  cudaLaunchConfig_t cfg;
+  memset((void*)&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  PNR_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  launch_counter()++;
+  return PNR_OK;
+}
+
+static int num_pairs(int tiles) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  int pairs = sms / 2;
+  return tiles < pairs ? tiles : pairs;
+}
+
+static int run_phases(const pnr_mlp& m, const Layout& L, const Plan& pl, int ns, long long P, float* out, int head,
+                      cudaStream_t st) {
+  // algorithmic work (2*MACs of the nn.Linear layers, unpadded)
+  const double mac_pre = (double)m.d_in * DH + (double)L.n_pre * m.d_latent * DH + 2.0 * L.n_pre * DH * DH;
+  const double mac_post = 2.0 * L.n_post * DH * DH + (double)DH * m.d_out;
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.w = (const uint8_t*)m.packed;
+  for (int b = 0; b < PNR_MAX_BLOCKS; ++b) {
+    p.off_g1[b] = L.off_g1[b];
+    p.off_g2[b] = L.off_g2[b];
+    p.off_g3[b] = L.off_g3[b];
+  }
+  p.off_biasA = L.off_biasA;
+  p.off_biasB = L.off_biasB;
+  p.off_bias0 = L.off_bias0;
+  p.off_lin_out = L.off_lin_out;
+  p.n_pre = L.n_pre;
+  p.n_post = L.n_post;
+  p.nks_z = L.nks_z;
+  p.nks_c = L.nks_c;
+  p.ns = ns;
+  p.ppw = pl.ppw;
+  p.P = P;
+  p.tilesA = pl.tilesA;
+  p.tilesB = pl.tilesB;
+  p.zc = pl.zc;
+  p.x3 = pl.x3;
+  p.out = out;
+  p.apply_head = head;
+  p.err = pl.err;
+  {
+    ProfScope ps(PROF_PHASE_A, 2.0 * mac_pre * (double)P * ns, 0.0, st);
+    PNR_TRY(launch_cluster(mlp_phaseA_kernel, num_pairs(pl.tilesA), p, st));
+  }
+  {
+    ProfScope ps(PROF_PHASE_B, 2.0 * mac_post * (double)P, 0.0, st);
+    PNR_TRY(launch_cluster(mlp_phaseB_kernel, num_pairs(pl.tilesB), p, st));
+  }
+  return PNR_OK;
+}
+
+int tc_check(cudaStream_t st) {
+  PNR_CUDA(cudaStreamSynchronize(st));
+  int v = 0;
+  PNR_CUDA(cudaMemcpyFromSymbol(&v, g_tc_err, sizeof(int)));
+  if (v != 0) {
+    int zero = 0;
+    cudaMemcpyToSymbol(g_tc_err, &zero, sizeof(int));
+    set_err("tensor-core MLP pipeline: barrier wait timed out (tag %d)", v);
+    return PNR_ERR_CUDA;
+  }
+  return PNR_OK;
+}
+
+size_t net_tc_workspace(const pnr_scene& sc, const pnr_mlp& m, int SB, long long P) {
+  if (tc_supported(m) != PNR_OK) return 256;
+  Layout L = make_layout(m);
+  return make_plan(L, sc.ns, (long long)SB * P, nullptr, 0).total;
+}
+
+int net_forward_tc(const pnr_scene& sc, const pnr_mlp& m, const float* xyz, const float* viewdirs, const float* rays,
+                   const float* z, int K, int SB, long long P, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  PNR_TRY(tc_supported(m));
+  PNR_CHECK_ARG(SB == 1, "net_forward_tc: one object per call");
+  PNR_UNSUPPORTED(sc.ns > 32, "more than 32 source views per object");
+  PNR_UNSUPPORTED(sc.feat_dtype != PNR_BF16, "bf16 path needs a bf16-packed pyramid");
+  for (int l = 0; l < sc.n_levels; ++l)
+    PNR_UNSUPPORTED(sc.C[l] % 8 != 0 || sc.ch_off[l] % 8 != 0, "bf16 gather needs channel counts that are multiples of 8");
+  PNR_CHECK_ARG(m.packed_bytes >= make_layout(m).total, "mlp.packed image too small");
+  Layout L = make_layout(m);
+  Plan pl = make_plan(L, sc.ns, P, ws, ws_bytes);
+  if (pl.total > ws_bytes + 256 || !ws) {
+    set_err("net_forward_tc: workspace too small (%zu < %zu)", ws_bytes, pl.total);
+    return PNR_ERR_WORKSPACE;
+  }
+  PNR_CUDA(cudaMemsetAsync(pl.err, 0, 16, st));
+  long long wrows = (long long)pl.tilesA * 128;
+  {
+    // algorithmic gather bytes: 4 taps x d_latent x 2 B per (point, view) + operand row written once
+    ProfScope ps(PROF_FEATURES, 0.0, (double)P * sc.ns * (4.0 * sc.d_latent * 2 + (double)pl.nsl * 128), st);
+    point_features_bf16_kernel<<<(unsigned)ceil_div_ll(wrows, 8), 256, 0, st>>>(sc, xyz, viewdirs, rays, z, K, P, pl.ppw,
+                                                                              pl.tilesA, L.nks_z, L.nks_c, pl.zc);
+    PNR_LAUNCHED();
+  }
+  return run_phases(m, L, pl, sc.ns, P, out, 1, st);
+}
+
+size_t mlp_tc_rows_workspace(const pnr_mlp& m, int SB, int NS, int P) {
+  if (tc_supported(m) != PNR_OK) return 256;
+  Layout L = make_layout(m);
+  return make_plan(L, NS, (long long)SB * P, nullptr, 0).total;
+}
+
+int mlp_forward_tc_rows(const pnr_mlp& m, const float* zx, int SB, int NS, int P, float* out, void* ws, size_t ws_bytes,
+                        cudaStream_t st) {
+  PNR_TRY(tc_supported(m));
+  PNR_UNSUPPORTED(NS > 32, "more than 32 source views per object");
+  Layout L = make_layout(m);
+  PNR_CHECK_ARG(m.packed_bytes >= L.total, "mlp.packed image too small");
+  long long pts = (long long)SB * P;
+  Plan pl = make_plan(L, NS, pts, ws, ws_bytes);
+  if (pl.total > ws_bytes + 256 || !ws) {
+    set_err("mlp_forward_tc: workspace too small (%zu < %zu)", ws_bytes, pl.total);
+    return PNR_ERR_WORKSPACE;
+  }
+  PNR_CUDA(cudaMemsetAsync(pl.err, 0, 16, st));
+  long long wrows = (long long)pl.tilesA * 128;
+  rows_to_operand_kernel<<<(unsigned)ceil_div_ll(wrows, 8), 256, 0, st>>>(zx, m.d_latent, m.d_in, SB, NS, P, pl.ppw,
+                                                                        pl.tilesA, L.nks_z, L.nks_c, pl.zc);
+  PNR_LAUNCHED();
+  return run_phases(m, L, pl, NS, pts, out, 0, st);
+}
+
+}  // namespace pnr
