@@ -60,6 +60,7 @@ int mlp_forward_tc_rows(const pnr_mlp& m, const float* zx, int SB, int NS, int P
                         size_t ws_bytes, cudaStream_t st);
 size_t mlp_tc_rows_workspace(const pnr_mlp& m, int SB, int NS, int P);
 int tc_check(cudaStream_t st);
+void tc_set_stats(unsigned long long* p);
 
 // pre-pool rows evaluated per internal chunk (bounds the scratch; rays are never split)
 static const long long kChunkRowsF32 = 1LL << 18;
@@ -211,6 +212,12 @@ int pnr_profile_end(double* ms, int64_t* launches, double* flops, double* bytes)
     delete r;
   }
   prof().recs.clear();
+  return PNR_OK;
+}
+
+// debug: device buffer of [74][16] cycle counters filled by the LAST phase-A launch (NULL = off)
+int pnr_tc_debug_stats(void* device_buffer) {
+  tc_set_stats((unsigned long long*)device_buffer);
   return PNR_OK;
 }
 

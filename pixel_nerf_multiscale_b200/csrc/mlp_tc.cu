@@ -24,6 +24,8 @@ using namespace ptx;
 // first barrier-timeout tag seen by any tensor-core kernel on this device (0 = none); read and
 // cleared by pnr_tc_check().  A protocol bug therefore fails loudly instead of hanging the GPU.
 __device__ int g_tc_err = 0;
+static thread_local unsigned long long* g_stats_ptr = nullptr;  // debug cycle counters (host pointer holder)
+void tc_set_stats(unsigned long long* p) { g_stats_ptr = p; }
 
 namespace tc {
 constexpr int DH = 512;                 // hidden width the tensor-core path is specialised for
@@ -32,6 +34,7 @@ constexpr int KS = 64;                  // K elements per slice
 constexpr int B_CHUNK = 128 * KS * 2;   // 16 KB: [8 k-groups][128 n-rows][8 bf16]
 constexpr int A_SLICE = ROWS * KS * 2;  // 8 KB : [8 k-groups][64 rows][8 bf16]
 constexpr int NB_ST = 5, NA_ST = 2;
+constexpr int B_SPLIT = 4;              // bulk copies per weight chunk
 constexpr int OFF_SX = 0;
 constexpr int OFF_H = OFF_SX + ROWS * DH * 2;
 constexpr int OFF_BRING = OFF_H + ROWS * DH * 2;
@@ -62,6 +65,7 @@ struct Params {
   float* out;                          // (P,4)
   int apply_head;
   int* err;
+  unsigned long long* stats;           // optional [pairs][16] cycle counters (debug)
 };
 }  // namespace tc
 using namespace tc;
@@ -347,18 +351,37 @@ struct Ctx {
   uint32_t tmem;
   uint32_t rank;
   int* err;
+  long long w[6];  // cycles spent waiting, by class (debug statistics)
   __device__ __forceinline__ uint32_t bar(int i) const { return bars + i * 8; }
 };
 
+__device__ __forceinline__ void twait(Ctx& cx, int cls, uint32_t bar, uint32_t parity, int tag) {
+  long long t0 = clock64();
+  mbar_wait(bar, parity, cx.err, tag);
+  cx.w[cls] += clock64() - t0;
+}
+
 // ---- producer side helpers ----------------------------------------------------------------------
-__device__ __forceinline__ void load_b(const Ctx& cx, Ring& rb, const uint8_t* src) {
-  mbar_wait(rb.empty_bar(), rb.phase ^ 1, cx.err, 201);
+__device__ __forceinline__ long long* ts_slot(int which, int idx) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  return reinterpret_cast<long long*>(smem_raw + OFF_BARS + 320) + which * NB_ST + idx;
+}
+__device__ __forceinline__ void load_b(Ctx& cx, Ring& rb, const uint8_t* src) {
+  twait(cx, 0, rb.empty_bar(), rb.phase ^ 1, 201);
+  {  // debug: commit -> producer-observed-empty latency
+    long long tc = *(volatile long long*)ts_slot(1, rb.idx);
+    if (tc != 0) { cx.w[2] += clock64() - tc; cx.w[3] += 1; }
+  }
   mbar_expect_tx(rb.full_bar(), B_CHUNK);
-  bulk_g2s(cx.smem + OFF_BRING + rb.idx * B_CHUNK, src, B_CHUNK, rb.full_bar());
+#pragma unroll
+  for (int q = 0; q < B_SPLIT; ++q)  // several smaller copies are serviced in parallel by the copy engine
+    bulk_g2s(cx.smem + OFF_BRING + rb.idx * B_CHUNK + q * (B_CHUNK / B_SPLIT), src + q * (B_CHUNK / B_SPLIT),
+             B_CHUNK / B_SPLIT, rb.full_bar());
+  *(volatile long long*)ts_slot(0, rb.idx) = clock64();
   rb.advance();
 }
-__device__ __forceinline__ void load_a(const Ctx& cx, Ring& ra, const uint8_t* src) {
-  mbar_wait(ra.empty_bar(), ra.phase ^ 1, cx.err, 202);
+__device__ __forceinline__ void load_a(Ctx& cx, Ring& ra, const uint8_t* src) {
+  twait(cx, 1, ra.empty_bar(), ra.phase ^ 1, 202);
   mbar_expect_tx(ra.full_bar(), A_SLICE);
   bulk_g2s(cx.smem + OFF_ARING + ra.idx * A_SLICE, src, A_SLICE, ra.full_bar());
   ra.advance();
@@ -369,40 +392,65 @@ __device__ __forceinline__ const uint8_t* wchunk(const Params& p, uint32_t off, 
 }
 
 // ---- MMA side helpers -----------------------------------------------------------------------------
+// Executed by ALL lanes of warp 1 in warp-uniform control flow (descriptors stay in uniform
+// registers; only the tcgen05 / arrive instructions themselves are issued by one elected lane).
 // Leader: waits for both CTAs' copies of the ring slot, issues 4 MMAs (K=64), releases the slot.
 // Peer:   waits for its own copy and relays the arrival to the leader's barrier.
-__device__ __forceinline__ void mma_step_b(const Ctx& cx, Ring& rb, uint32_t a_addr, uint32_t d_col, bool first) {
-  mbar_wait(rb.full_bar(), rb.phase, cx.err, 301);
+__device__ __forceinline__ void mma_step_b(Ctx& cx, Ring& rb, uint32_t a_addr, uint32_t d_col, bool first) {
+  twait(cx, 0, rb.full_bar(), rb.phase, 301);
   if (cx.rank == 0) {
+    {  // debug: bulk-copy issue -> MMA-observed-full latency (includes the peer relay)
+      long long ti = *(volatile long long*)ts_slot(0, rb.idx);
+      long long d = clock64() - ti;
+      cx.w[5] += d;
+    }
     tc_fence_after();
     const uint32_t idesc = idesc_bf16_f32(128, 256);
     const uint32_t b_addr = cx.smem + OFF_BRING + rb.idx * B_CHUNK;
+    const uint64_t da0 = smem_desc(a_addr, ROWS * 16, 128);
+    const uint64_t db0 = smem_desc(b_addr, 128 * 16, 128);
+    const uint32_t dcol = cx.tmem + d_col;
+    const uint32_t ebar = rb.empty_bar();
+    if (elect_one()) {
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      uint64_t da = smem_desc(a_addr + kk * 2 * (ROWS * 16), ROWS * 16, 128);
-      uint64_t db = smem_desc(b_addr + kk * 2 * (128 * 16), 128 * 16, 128);
-      mma_bf16<2>(cx.tmem + d_col, da, db, idesc, (first && kk == 0) ? 0u : 1u);
+      for (int kk = 0; kk < 4; ++kk) {
+        // advancing K by 16 elements = 2 core-matrix panels: add to the (addr>>4) field only
+        mma_bf16<2>(dcol, da0 + (uint64_t)(kk * 2 * (ROWS * 16) >> 4), db0 + (uint64_t)(kk * 2 * (128 * 16) >> 4), idesc,
+                    (first && kk == 0) ? 0u : 1u);
+      }
+      mma_commit<2>(ebar, 0x3);
+      *(volatile long long*)ts_slot(1, rb.idx) = clock64();
     }
-    mma_commit<2>(rb.empty_bar(), 0x3);
+    __syncwarp();
   } else {
-    mbar_arrive_cluster(rb.full_bar(), 0);
+    if (elect_one()) mbar_arrive_cluster(rb.full_bar(), 0);
+    __syncwarp();
   }
   rb.advance();
 }
-__device__ __forceinline__ void a_wait(const Ctx& cx, Ring& ra) {
-  mbar_wait(ra.full_bar(), ra.phase, cx.err, 302);
-  if (cx.rank != 0) mbar_arrive_cluster(ra.full_bar(), 0);
+__device__ __forceinline__ void a_wait(Ctx& cx, Ring& ra) {
+  twait(cx, 1, ra.full_bar(), ra.phase, 302);
+  if (cx.rank != 0) {
+    if (elect_one()) mbar_arrive_cluster(ra.full_bar(), 0);
+    __syncwarp();
+  }
 }
 __device__ __forceinline__ void a_release(const Ctx& cx, Ring& ra) {
-  if (cx.rank == 0) mma_commit<2>(ra.empty_bar(), 0x3);
+  if (cx.rank == 0) {
+    if (elect_one()) mma_commit<2>(ra.empty_bar(), 0x3);
+    __syncwarp();
+  }
   ra.advance();
 }
 __device__ __forceinline__ void signal(const Ctx& cx, int bar_idx) {
-  if (cx.rank == 0) mma_commit<2>(cx.bar(bar_idx), 0x3);
+  if (cx.rank == 0) {
+    if (elect_one()) mma_commit<2>(cx.bar(bar_idx), 0x3);
+    __syncwarp();
+  }
 }
 
 // x[:, all 512] (+)= A_ring @ W^T over `nks` slices (k-outer).  first_acc0: overwrite on slice 0.
-__device__ __forceinline__ void gemm_from_ring(const Ctx& cx, Ring& ra, Ring& rb, int nks, uint32_t xcol, bool overwrite) {
+__device__ __forceinline__ void gemm_from_ring(Ctx& cx, Ring& ra, Ring& rb, int nks, uint32_t xcol, bool overwrite) {
   for (int s = 0; s < nks; ++s) {
     a_wait(cx, ra);
     uint32_t a_addr = cx.smem + OFF_ARING + ra.idx * A_SLICE;
@@ -411,19 +459,19 @@ __device__ __forceinline__ void gemm_from_ring(const Ctx& cx, Ring& ra, Ring& rb
   }
 }
 // NET = S_x @ W0^T, n-outer; waits for operand slices as the epilogue publishes them
-__device__ __forceinline__ void gemm_fc0(const Ctx& cx, Ring& rb, uint32_t netcol, uint32_t sx_phase) {
+__device__ __forceinline__ void gemm_fc0(Ctx& cx, Ring& rb, uint32_t netcol, uint32_t sx_phase) {
   for (int nb = 0; nb < 2; ++nb) {
     for (int s = 0; s < DH / KS; ++s) {
-      if (nb == 0 && cx.rank == 0) mbar_wait(cx.bar(SX_READY + s), sx_phase, cx.err, 310 + s);
+      if (nb == 0 && cx.rank == 0) twait(cx, 2, cx.bar(SX_READY + s), sx_phase, 310 + s);
       mma_step_b(cx, rb, cx.smem + OFF_SX + s * A_SLICE, netcol + nb * 128, s == 0);
     }
     signal(cx, NET_READY + nb);
   }
 }
 // X += H @ W1^T, k-outer
-__device__ __forceinline__ void gemm_fc1(const Ctx& cx, Ring& rb, uint32_t xcol, uint32_t h_phase) {
+__device__ __forceinline__ void gemm_fc1(Ctx& cx, Ring& rb, uint32_t xcol, uint32_t h_phase) {
   for (int s = 0; s < DH / KS; ++s) {
-    if (cx.rank == 0) mbar_wait(cx.bar(H_READY + s), h_phase, cx.err, 320 + s);
+    if (cx.rank == 0) twait(cx, 3, cx.bar(H_READY + s), h_phase, 320 + s);
     for (int nb = 0; nb < 2; ++nb) mma_step_b(cx, rb, cx.smem + OFF_H + s * A_SLICE, xcol + nb * 128, false);
   }
 }
@@ -485,6 +533,7 @@ __device__ __forceinline__ void setup_barriers(const Ctx& cx) {
   mbar_init(cx.bar(NET_READY + 1), 1);
   for (int i = 0; i < 8; ++i) { mbar_init(cx.bar(SX_READY + i), 4); mbar_init(cx.bar(H_READY + i), 4); }
   mbar_init(cx.bar(XP_DONE), 16);
+  for (int i = 0; i < 2 * NB_ST; ++i) *ts_slot(i / NB_ST, i % NB_ST) = 0;
   fence_mbar_init();
 }
 
@@ -498,6 +547,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
   cx.bars = cx.smem + OFF_BARS;
   cx.rank = cluster_ctarank();
   cx.err = &g_tc_err;
+  for (int i = 0; i < 6; ++i) cx.w[i] = 0;
+  const long long t_begin = clock64();
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + OFF_BARS + N_BARS * 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) setup_barriers(cx);
@@ -536,10 +587,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
             for (int nb = 0; nb < 2; ++nb) load_b(cx, rb, wchunk(p, p.off_g3[b], s, nb, cx.rank));
         }
       }
+      if (p.stats && cx.rank == 0) {
+        unsigned long long* st = p.stats + (size_t)pair * 16;
+        st[6] = clock64() - t_begin;
+        st[7] = cx.w[0];
+        st[8] = cx.w[1];
+        st[15] = cx.w[3] ? cx.w[2] / cx.w[3] : 0;  // mean commit -> empty-observed latency
+      }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader) / relay (peer) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (leader) / relay (peer): whole warp, uniform ==========
+    {
       Ring ra, rb;
       ra.init(cx.bar(A_FULL), cx.bar(A_EMPTY), NA_ST);
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST);
@@ -550,12 +608,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
         gemm_from_ring(cx, ra, rb, nsl, xcol, true);
         signal(cx, X_READY);
         for (int b = 0; b < p.n_pre; ++b, ++use) {
-          if (b == 0 && it > 0 && cx.rank == 0) mbar_wait(cx.bar(XP_DONE), (it - 1) & 1, cx.err, 330);
+          if (b == 0 && it > 0 && cx.rank == 0) twait(cx, 4, cx.bar(XP_DONE), (it - 1) & 1, 330);
           gemm_fc0(cx, rb, netcol, use & 1);
           if (b + 1 < p.n_pre) gemm_from_ring(cx, ra, rb, p.nks_z, xcol, false);
           gemm_fc1(cx, rb, xcol, use & 1);
           signal(cx, X_READY);
         }
+      }
+      if (p.stats && cx.rank == 0 && lane == 0) {
+        unsigned long long* st = p.stats + (size_t)pair * 16;
+        st[0] = clock64() - t_begin;
+        for (int i = 0; i < 5; ++i) st[1 + i] = cx.w[i];
+        p.stats[74 * 16 + pair] = cx.w[5];  // sum of issue -> full-observed latencies
       }
     }
   } else if (warp >= 4) {
@@ -567,27 +631,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
     for (int tile = pair; tile < p.tilesA; tile += npairs, ++it) {
       const uint32_t xcol = (it & 1) ? 256u : 0u, netcol = 256u - xcol;
       for (int b = 0; b < p.n_pre; ++b) {
-        mbar_wait(cx.bar(X_READY), xph, cx.err, 401);
+        twait(cx, 0, cx.bar(X_READY), xph, 401);
         xph ^= 1;
         tc_fence_after();
+        long long t0 = clock64();
         for (int nb = 0; nb < 2; ++nb) epi_to_operand(cx, e, xcol, nb, biasA + (size_t)b * DH, OFF_SX, SX_READY);
+        cx.w[2] += clock64() - t0;
         for (int nb = 0; nb < 2; ++nb) {
-          mbar_wait(cx.bar(NET_READY + nb), nph, cx.err, 402 + nb);
+          twait(cx, 1, cx.bar(NET_READY + nb), nph, 402 + nb);
           tc_fence_after();
+          t0 = clock64();
           epi_to_operand(cx, e, netcol, nb, bias0 + (size_t)b * DH, OFF_H, H_READY);
+          cx.w[3] += clock64() - t0;
         }
         nph ^= 1;
       }
       // ---- view mean-pool of the residual stream -> pooled x (fp32) in phase-B tile order ----
-      mbar_wait(cx.bar(X_READY), xph, cx.err, 405);
+      twait(cx, 0, cx.bar(X_READY), xph, 405);
       xph ^= 1;
       tc_fence_after();
+      const long long tp0 = clock64();
       int v;
       bool valid;
       long long gp = tileA_point(tile, (int)cx.rank, e.row, p.ns, p.ppw, v, valid);
       valid = valid && v == 0 && gp < p.P;
       const float* bP = biasA + (size_t)p.n_pre * DH;
-      const float inv = (float)p.ns;
+      const float inv = 1.0f / (float)p.ns;
+      const long long tb = gp >> 7;
+      const int cb = (int)((gp >> 6) & 1), rb_ = (int)(gp & 63);
       for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -595,27 +666,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
           tmem_ld32(cx.tmem + e.lane_addr + xcol + nb * 128 + e.cs * 64 + half * 32, r);
           tmem_ld_wait();
           const int f0 = feat0(e, nb, half);
-          float acc[32];
+          // x3[tileB][ctaB][nb][h][jq (32)][row (64)][4]
+          float4* dst = reinterpret_cast<float4*>(p.x3) +
+                        ((((tb * 2 + cb) * 2 + nb) * 2 + e.h) * 32 + (e.cs * 16 + half * 8)) * 64 + rb_;
+          const float4* b4 = reinterpret_cast<const float4*>(bP + f0);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float x = __uint_as_float(r[i]);
-            float s = x;
-            for (int k = 1; k < p.ns; ++k) s += __shfl_down_sync(0xffffffffu, x, k);
-            acc[i] = s / inv + __ldg(bP + f0 + i);
-          }
-          if (valid) {
-            const long long tb = gp >> 7;
-            const int cb = (int)((gp >> 6) & 1), rb_ = (int)(gp & 63);
-            // x3[tileB][ctaB][nb][h][jq (32)][row (64)][4]
-            float4* dst = reinterpret_cast<float4*>(p.x3) +
-                          ((((tb * 2 + cb) * 2 + nb) * 2 + e.h) * 32 + (e.cs * 16 + half * 8)) * 64 + rb_;
+          for (int j = 0; j < 8; ++j) {
+            float s4[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[(size_t)j * 64] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            for (int i = 0; i < 4; ++i) {
+              float x = __uint_as_float(r[4 * j + i]);
+              float s = x;
+              if (p.ns > 1) s += __shfl_down_sync(0xffffffffu, x, 1);
+              if (p.ns > 2) s += __shfl_down_sync(0xffffffffu, x, 2);
+              for (int k = 3; k < p.ns; ++k) s += __shfl_down_sync(0xffffffffu, x, k);
+              s4[i] = s * inv;
+            }
+            if (valid) {
+              float4 bb = __ldg(b4 + j);
+              dst[(size_t)j * 64] = make_float4(s4[0] + bb.x, s4[1] + bb.y, s4[2] + bb.z, s4[3] + bb.w);
+            }
           }
         }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(cx.bar(XP_DONE), 0);
+      cx.w[4] += clock64() - tp0;
+    }
+    if (p.stats && cx.rank == 0 && warp == 4 && lane == 0) {
+      unsigned long long* st = p.stats + (size_t)pair * 16;
+      st[9] = clock64() - t_begin;
+      for (int i = 0; i < 5; ++i) st[10 + i] = cx.w[i];
     }
   }
   __syncwarp();
@@ -634,6 +715,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
   cx.bars = cx.smem + OFF_BARS;
   cx.rank = cluster_ctarank();
   cx.err = &g_tc_err;
+  for (int i = 0; i < 6; ++i) cx.w[i] = 0;
+  const long long t_begin = clock64();
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + OFF_BARS + N_BARS * 8);
   float* s_wout = reinterpret_cast<float*>(smem_raw + OFF_ARING);          // [4][512] + [4]
   float* s_part = s_wout + 4 * DH + 4;                                    // [4 outputs][4 parts][64 rows]
@@ -669,7 +752,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
         }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       Ring rb;
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST);
       uint32_t use = 0;
@@ -863,6 +946,7 @@ static int run_phases(const pnr_mlp& m, const Layout& L, const Plan& pl, int ns,
   p.out = out;
   p.apply_head = head;
   p.err = pl.err;
+  p.stats = g_stats_ptr;
   {
     ProfScope ps(PROF_PHASE_A, 2.0 * mac_pre * (double)P * ns, 0.0, st);
     PNR_TRY(launch_cluster(mlp_phaseA_kernel, num_pairs(pl.tilesA), p, st));

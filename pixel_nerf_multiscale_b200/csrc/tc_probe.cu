@@ -15,7 +15,7 @@
 namespace pnr {
 using namespace ptx;
 
-template <int CG>
+template <int CG, bool REMOTE = false>
 __global__ void __launch_bounds__(128) probe_gemm_kernel(const __nv_bfloat16* __restrict__ A,
                                                          const __nv_bfloat16* __restrict__ B, float* __restrict__ D,
                                                          int K, int* __restrict__ err) {
@@ -47,19 +47,27 @@ __global__ void __launch_bounds__(128) probe_gemm_kernel(const __nv_bfloat16* __
   const uint32_t tmem = *tmem_slot;
 
   const uint32_t bytesA = ROWS_A * K * 2, bytesB = ROWS_B * K * 2;
-  if (threadIdx.x == 0) {
+  if (REMOTE) {
+    // experiment: the peer's bulk copies complete on the LEADER's barrier (no relay hop)
+    if (threadIdx.x == 0) {
+      if (rank == 0) mbar_expect_tx(bar_full, 2 * (bytesA + bytesB));
+      uint32_t lead_bar = mapa(bar_full, 0);
+      bulk_g2s(smem_u32(sA), A + (size_t)rank * ROWS_A * K, bytesA, rank == 0 ? bar_full : lead_bar);
+      bulk_g2s(smem_u32(sB), B + (size_t)rank * ROWS_B * K, bytesB, rank == 0 ? bar_full : lead_bar);
+    }
+  } else if (threadIdx.x == 0) {
     mbar_expect_tx(bar_full, bytesA + bytesB);
     bulk_g2s(smem_u32(sA), A + (size_t)rank * ROWS_A * K, bytesA, bar_full);
     bulk_g2s(smem_u32(sB), B + (size_t)rank * ROWS_B * K, bytesB, bar_full);
   }
-  if (CG == 2 && rank == 1 && threadIdx.x == 32) {
+  if (!REMOTE && CG == 2 && rank == 1 && threadIdx.x == 32) {
     // relay: peer operands landed -> tell the leader
     mbar_wait(bar_full, 0, err, 101);
     mbar_arrive_cluster(bar_peer, 0);
   }
   if (rank == 0 && threadIdx.x == 32) {
     mbar_wait(bar_full, 0, err, 102);
-    if (CG == 2) mbar_wait(bar_peer, 0, err, 103);
+    if (CG == 2 && !REMOTE) mbar_wait(bar_peer, 0, err, 103);
     tc_fence_after();
     const uint32_t idesc = idesc_bf16_f32(128, 256);
     for (int k = 0; k < K / 16; ++k) {
@@ -102,9 +110,10 @@ extern "C" int pnr_tc_probe(int mode, const void* A, const void* B, float* D, in
     PNR_LAUNCHED();
     return PNR_OK;
   }
-  if (mode == 2) {
+  if (mode == 2 || mode == 3) {
     size_t smem = (size_t)(64 + 128) * K * 2 + 64;
-    PNR_CUDA(cudaFuncSetAttribute(probe_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = mode == 2 ? probe_gemm_kernel<2, false> : probe_gemm_kernel<2, true>;
+    PNR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg;
     memset((void*)&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2);
@@ -118,7 +127,7 @@ extern "C" int pnr_tc_probe(int mode, const void* A, const void* B, float* D, in
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PNR_CUDA(cudaLaunchKernelEx(&cfg, probe_gemm_kernel<2>, (const __nv_bfloat16*)A, (const __nv_bfloat16*)B, D, K, err));
+    PNR_CUDA(cudaLaunchKernelEx(&cfg, kern, (const __nv_bfloat16*)A, (const __nv_bfloat16*)B, D, K, err));
     pnr::launch_counter()++;
     return PNR_OK;
   }

@@ -30,6 +30,15 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local, uint32_t rank) {
   return r;
 }
 
+// one lane of a converged warp (warp-uniform control flow around it keeps operands in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -41,7 +50,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // arrive on a barrier that lives in CTA `rank` of the cluster (may be this CTA)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_local, uint32_t rank) {
   uint32_t remote = mapa(bar_local, rank);
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  // default (.release.cta) semantics, like CUTLASS's ClusterBarrier::arrive(cta_id): an explicit
+  // .release.cluster costs a full memory barrier (ERRBAR/MEMBAR, >1000 cycles) per arrive, which
+  // serialised the peer->leader relay to one ring slot per ~1300 cycles in the first version.
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -50,7 +62,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
@@ -61,10 +73,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // *err (global) and the wait returns; the kernel then runs to completion with garbage results and
 // the host reports the failure.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int tag) {
-  if (mbar_try_wait(bar, parity)) return;
-  for (uint32_t it = 0; it < (1u << 22); ++it) {
+  // try_wait itself suspends the thread for a hardware-bounded interval, so this loop does not
+  // spin hot.  (Default .acquire.cta semantics on purpose: a cluster-scope acquire makes ptxas emit
+  // CCTL.IVALL -- a full L1 invalidate -- after every probe, which dominated the first profile.)
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
     if (mbar_try_wait(bar, parity)) return;
-    if (it > 64) __nanosleep(64);
   }
   if (err) atomicCAS(err, 0, tag);
 }

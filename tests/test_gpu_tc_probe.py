@@ -29,11 +29,12 @@ def _probe(mode, A, B, K):
     fn.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     ncols = 256 if mode == 1 else 128
     ncta = 1 if mode == 1 else 2
+    mode_in, mode = mode, (2 if mode == 3 else mode)
     a_img = _panels(A, 128 if mode == 1 else 64).cuda()
     b_img = _panels(B, 256 if mode == 1 else 128).cuda()
     D = torch.full((ncta, 128, ncols), float("nan"), device="cuda")
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
-    N.check(fn(mode, N.ptr(a_img), N.ptr(b_img), N.ptr(D), K, N.ptr(err), N.stream_ptr(D.device)), "pnr_tc_probe")
+    N.check(fn(mode_in, N.ptr(a_img), N.ptr(b_img), N.ptr(D), K, N.ptr(err), N.stream_ptr(D.device)), "pnr_tc_probe")
     torch.cuda.synchronize()
     return D.cpu(), int(err.item())
 
