@@ -15,6 +15,8 @@
 // Phase B (rows = points): remaining blocks, lin_out, sigmoid/relu head (models.py.backup2:274-281).
 // The [latent|code] operand rows are produced by the bf16 variant of kernel (a) below
 // (128-bit gathers of the NHWC bf16 pyramid, written directly in UMMA panel order).
+#include <cuda.h>
+
 #include "features.cuh"
 #include "tc_ptx.cuh"
 
@@ -23,9 +25,22 @@ using namespace ptx;
 
 // first barrier-timeout tag seen by any tensor-core kernel on this device (0 = none); read and
 // cleared by pnr_tc_check().  A protocol bug therefore fails loudly instead of hanging the GPU.
-__device__ int g_tc_err = 0;
+// The word lives in mapped pinned host memory so that it can be read even after the kernel trapped.
+static int* g_err_host = nullptr;   // host view
+static int* g_err_dev = nullptr;    // device view of the same word
+static int ensure_err_word() {
+  if (g_err_host) return PNR_OK;
+  PNR_CUDA(cudaHostAlloc((void**)&g_err_host, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+  g_err_host[0] = 0;
+  PNR_CUDA(cudaHostGetDevicePointer((void**)&g_err_dev, g_err_host, 0));
+  return PNR_OK;
+}
 static thread_local unsigned long long* g_stats_ptr = nullptr;  // debug cycle counters (host pointer holder)
 void tc_set_stats(unsigned long long* p) { g_stats_ptr = p; }
+
+#ifndef PNR_TC_STATS
+#define PNR_TC_STATS 0  // 1: per-role cycle counters (tools/tc_stats.py); costs ~10% of the MMA issue rate
+#endif
 
 namespace tc {
 constexpr int DH = 512;                 // hidden width the tensor-core path is specialised for
@@ -34,7 +49,10 @@ constexpr int KS = 64;                  // K elements per slice
 constexpr int B_CHUNK = 128 * KS * 2;   // 16 KB: [8 k-groups][128 n-rows][8 bf16]
 constexpr int A_SLICE = ROWS * KS * 2;  // 8 KB : [8 k-groups][64 rows][8 bf16]
 constexpr int NB_ST = 5, NA_ST = 2;
-constexpr int B_SPLIT = 4;              // bulk copies per weight chunk
+constexpr int B_SPLIT = 8;              // TMA boxes per weight chunk (2 KB each: small boxes land sooner)
+constexpr int A_SPLIT = 4;              // TMA boxes per operand slice
+constexpr int W_REPLICAS = 4;           // copies of the packed weights; pair p streams copy p % W_REPLICAS so that
+                                        // 74 pairs do not all hit the same L2 lines at the same time
 constexpr int OFF_SX = 0;
 constexpr int OFF_H = OFF_SX + ROWS * DH * 2;
 constexpr int OFF_BRING = OFF_H + ROWS * DH * 2;
@@ -46,7 +64,7 @@ static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
 // barrier indices (uint64 each)
 constexpr int B_FULL = 0, B_EMPTY = B_FULL + NB_ST, A_FULL = B_EMPTY + NB_ST, A_EMPTY = A_FULL + NA_ST,
-              X_READY = A_EMPTY + NA_ST, NET_READY = X_READY + 1, SX_READY = NET_READY + 2, H_READY = SX_READY + 8,
+              X_READY = A_EMPTY + NA_ST, NET_READY = X_READY + 2, SX_READY = NET_READY + 2, H_READY = SX_READY + 8,
               XP_DONE = H_READY + 8, N_BARS = XP_DONE + 1;
 
 struct Params {
@@ -60,12 +78,15 @@ struct Params {
   int ns, ppw;                         // views per point, points per 32-row group
   long long P;                         // points
   int tilesA, tilesB;
+  uint32_t replica_stride;             // bytes between weight replicas
   const uint8_t* zc;                   // [tileA][cta][slice][A_SLICE]
   float* x3;                           // pooled residual stream, phase-B tile order
   float* out;                          // (P,4)
   int apply_head;
   int* err;
   unsigned long long* stats;           // optional [pairs][16] cycle counters (debug)
+  CUtensorMap tm_w;                    // packed weights as rows of 256 B, box = 16 rows (4 KB)
+  CUtensorMap tm_zc;                   // operand image as rows of 256 B, box = 32 rows (8 KB)
 };
 }  // namespace tc
 using namespace tc;
@@ -170,13 +191,14 @@ static Layout make_layout(const pnr_mlp& m) {
 
 size_t mlp_tc_packed_bytes(const pnr_mlp& m) {
   if (tc_supported(m) != PNR_OK) return 256;
-  return make_layout(m).total;
+  return make_layout(m).total * W_REPLICAS;
 }
 
 int mlp_tc_pack(const pnr_mlp& m, void* dst, size_t dst_bytes, cudaStream_t st) {
   PNR_TRY(tc_supported(m));
   Layout L = make_layout(m);
-  PNR_CHECK_ARG(dst_bytes >= L.total, "mlp_pack: destination too small (%zu < %zu)", dst_bytes, L.total);
+  PNR_CHECK_ARG(dst_bytes >= L.total * W_REPLICAS, "mlp_pack: destination too small (%zu < %zu)", dst_bytes,
+                L.total * W_REPLICAS);
   PNR_CHECK_ARG(((uintptr_t)dst & 15) == 0, "mlp_pack: destination must be 16-byte aligned");
   uint8_t* d = (uint8_t*)dst;
   auto pack = [&](const float* w, int K, int slices, uint32_t off) -> int {
@@ -214,6 +236,8 @@ int mlp_tc_pack(const pnr_mlp& m, void* dst, size_t dst_bytes, cudaStream_t st) 
   for (int b = 0; b < m.n_blocks; ++b) PNR_TRY(bias(m.fc0_b[b], nullptr, nullptr, nullptr, bias0 + (size_t)b * DH));
   PNR_CUDA(cudaMemcpyAsync(d + L.off_lin_out, m.lin_out_w, (size_t)4 * DH * 4, cudaMemcpyDeviceToDevice, st));
   PNR_CUDA(cudaMemcpyAsync(d + L.off_lin_out + (size_t)4 * DH * 4, m.lin_out_b, 16, cudaMemcpyDeviceToDevice, st));
+  for (int r = 1; r < W_REPLICAS; ++r)
+    PNR_CUDA(cudaMemcpyAsync(d + (size_t)r * L.total, d, L.total, cudaMemcpyDeviceToDevice, st));
   return PNR_OK;
 }
 
@@ -356,9 +380,13 @@ struct Ctx {
 };
 
 __device__ __forceinline__ void twait(Ctx& cx, int cls, uint32_t bar, uint32_t parity, int tag) {
+#if PNR_TC_STATS
   long long t0 = clock64();
   mbar_wait(bar, parity, cx.err, tag);
   cx.w[cls] += clock64() - t0;
+#else
+  mbar_wait(bar, parity, cx.err, tag);
+#endif
 }
 
 // ---- producer side helpers ----------------------------------------------------------------------
@@ -366,44 +394,58 @@ __device__ __forceinline__ long long* ts_slot(int which, int idx) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   return reinterpret_cast<long long*>(smem_raw + OFF_BARS + 320) + which * NB_ST + idx;
 }
-__device__ __forceinline__ void load_b(Ctx& cx, Ring& rb, const uint8_t* src) {
+// Weight chunk / operand slice loads: 2-D tiled TMA whose transaction bytes complete on the LEADER
+// CTA's full barrier (no peer->leader relay hop).  The leader expects both CTAs' bytes.
+__device__ __forceinline__ void load_b(Ctx& cx, Ring& rb, const CUtensorMap* tm, uint32_t byte_off) {
   twait(cx, 0, rb.empty_bar(), rb.phase ^ 1, 201);
-  {  // debug: commit -> producer-observed-empty latency
+#if PNR_TC_STATS
+  {  // commit -> producer-observed-empty latency
     long long tc = *(volatile long long*)ts_slot(1, rb.idx);
     if (tc != 0) { cx.w[2] += clock64() - tc; cx.w[3] += 1; }
   }
-  mbar_expect_tx(rb.full_bar(), B_CHUNK);
+#endif
+  const int row0 = (int)(byte_off >> 8);
+  const uint32_t dst = cx.smem + OFF_BRING + rb.idx * B_CHUNK, fb = rb.full_bar();
+  if (elect_one()) {  // operands computed in warp-uniform code -> uniform registers, no R2UR waterfall
+    if (cx.rank == 0) mbar_expect_tx(fb, 2 * B_CHUNK);
 #pragma unroll
-  for (int q = 0; q < B_SPLIT; ++q)  // several smaller copies are serviced in parallel by the copy engine
-    bulk_g2s(cx.smem + OFF_BRING + rb.idx * B_CHUNK + q * (B_CHUNK / B_SPLIT), src + q * (B_CHUNK / B_SPLIT),
-             B_CHUNK / B_SPLIT, rb.full_bar());
-  *(volatile long long*)ts_slot(0, rb.idx) = clock64();
+    for (int q = 0; q < B_SPLIT; ++q)
+      tma_load_2d_pair(dst + q * (B_CHUNK / B_SPLIT), tm, 0, row0 + q * (B_CHUNK / B_SPLIT / 256), fb);
+#if PNR_TC_STATS
+    *(volatile long long*)ts_slot(0, rb.idx) = clock64();
+#endif
+  }
+  __syncwarp();
   rb.advance();
 }
-__device__ __forceinline__ void load_a(Ctx& cx, Ring& ra, const uint8_t* src) {
+__device__ __forceinline__ void load_a(Ctx& cx, Ring& ra, const CUtensorMap* tm, size_t byte_off) {
   twait(cx, 1, ra.empty_bar(), ra.phase ^ 1, 202);
-  mbar_expect_tx(ra.full_bar(), A_SLICE);
-  bulk_g2s(cx.smem + OFF_ARING + ra.idx * A_SLICE, src, A_SLICE, ra.full_bar());
+  const uint32_t dst = cx.smem + OFF_ARING + ra.idx * A_SLICE, fb = ra.full_bar();
+  if (elect_one()) {
+    if (cx.rank == 0) mbar_expect_tx(fb, 2 * A_SLICE);
+#pragma unroll
+    for (int q = 0; q < A_SPLIT; ++q)
+      tma_load_2d_pair(dst + q * (A_SLICE / A_SPLIT), tm, 0, (int)(byte_off >> 8) + q * (A_SLICE / A_SPLIT / 256), fb);
+  }
+  __syncwarp();
   ra.advance();
 }
 // weight chunk (slice s, column block nb) of a GEMM group for this CTA
-__device__ __forceinline__ const uint8_t* wchunk(const Params& p, uint32_t off, int s, int nb, uint32_t rank) {
-  return p.w + off + (size_t)((s * 2 + nb) * 2 + rank) * B_CHUNK;
+__device__ __forceinline__ uint32_t wchunk(uint32_t off, int s, int nb, uint32_t rank) {
+  return off + (uint32_t)((s * 2 + nb) * 2 + rank) * B_CHUNK;  // + replica base, added by the caller's `wb`
 }
 
 // ---- MMA side helpers -----------------------------------------------------------------------------
 // Executed by ALL lanes of warp 1 in warp-uniform control flow (descriptors stay in uniform
 // registers; only the tcgen05 / arrive instructions themselves are issued by one elected lane).
-// Leader: waits for both CTAs' copies of the ring slot, issues 4 MMAs (K=64), releases the slot.
-// Peer:   waits for its own copy and relays the arrival to the leader's barrier.
+// Only the leader CTA runs this role: waits until both CTAs' copies of the ring slot have landed
+// (both complete on its barrier), issues 4 MMAs (K=64) and releases the slot in both CTAs.
 __device__ __forceinline__ void mma_step_b(Ctx& cx, Ring& rb, uint32_t a_addr, uint32_t d_col, bool first) {
   twait(cx, 0, rb.full_bar(), rb.phase, 301);
   if (cx.rank == 0) {
-    {  // debug: bulk-copy issue -> MMA-observed-full latency (includes the peer relay)
-      long long ti = *(volatile long long*)ts_slot(0, rb.idx);
-      long long d = clock64() - ti;
-      cx.w[5] += d;
-    }
+#if PNR_TC_STATS
+    cx.w[5] += clock64() - *(volatile long long*)ts_slot(0, rb.idx);  // load issue -> MMA-observed-full
+#endif
     tc_fence_after();
     const uint32_t idesc = idesc_bf16_f32(128, 256);
     const uint32_t b_addr = cx.smem + OFF_BRING + rb.idx * B_CHUNK;
@@ -419,22 +461,15 @@ __device__ __forceinline__ void mma_step_b(Ctx& cx, Ring& rb, uint32_t a_addr, u
                     (first && kk == 0) ? 0u : 1u);
       }
       mma_commit<2>(ebar, 0x3);
+#if PNR_TC_STATS
       *(volatile long long*)ts_slot(1, rb.idx) = clock64();
+#endif
     }
-    __syncwarp();
-  } else {
-    if (elect_one()) mbar_arrive_cluster(rb.full_bar(), 0);
     __syncwarp();
   }
   rb.advance();
 }
-__device__ __forceinline__ void a_wait(Ctx& cx, Ring& ra) {
-  twait(cx, 1, ra.full_bar(), ra.phase, 302);
-  if (cx.rank != 0) {
-    if (elect_one()) mbar_arrive_cluster(ra.full_bar(), 0);
-    __syncwarp();
-  }
-}
+__device__ __forceinline__ void a_wait(Ctx& cx, Ring& ra) { twait(cx, 1, ra.full_bar(), ra.phase, 302); }
 __device__ __forceinline__ void a_release(const Ctx& cx, Ring& ra) {
   if (cx.rank == 0) {
     if (elect_one()) mma_commit<2>(ra.empty_bar(), 0x3);
@@ -468,12 +503,18 @@ __device__ __forceinline__ void gemm_fc0(Ctx& cx, Ring& rb, uint32_t netcol, uin
     signal(cx, NET_READY + nb);
   }
 }
-// X += H @ W1^T, k-outer
+// X += H @ W1^T in four quarters (s 0-3 | nb 0,1), (s 4-7 | nb 0,1): the first half of X's columns
+// is final one quarter before the end, so its epilogue overlaps the last quarter, and the second
+// half of H is only needed from the third quarter on.  The producer streams chunks in this order.
 __device__ __forceinline__ void gemm_fc1(Ctx& cx, Ring& rb, uint32_t xcol, uint32_t h_phase) {
-  for (int s = 0; s < DH / KS; ++s) {
-    if (cx.rank == 0) twait(cx, 3, cx.bar(H_READY + s), h_phase, 320 + s);
-    for (int nb = 0; nb < 2; ++nb) mma_step_b(cx, rb, cx.smem + OFF_H + s * A_SLICE, xcol + nb * 128, false);
-  }
+  for (int sh = 0; sh < 2; ++sh)
+    for (int nb = 0; nb < 2; ++nb) {
+      for (int s = sh * 4; s < sh * 4 + 4; ++s) {
+        if (nb == 0) twait(cx, 3, cx.bar(H_READY + s), h_phase, 320 + s);
+        mma_step_b(cx, rb, cx.smem + OFF_H + s * A_SLICE, xcol + nb * 128, false);
+      }
+      if (sh == 1) signal(cx, X_READY + nb);
+    }
 }
 
 // ---- epilogue helpers -------------------------------------------------------------------------------
@@ -525,10 +566,10 @@ __device__ __forceinline__ void epi_to_operand(const Ctx& cx, const Epi& e, uint
 }
 
 __device__ __forceinline__ void setup_barriers(const Ctx& cx) {
-  const uint32_t full_cnt = cx.rank == 0 ? 2 : 1;
-  for (int i = 0; i < NB_ST; ++i) { mbar_init(cx.bar(B_FULL + i), full_cnt); mbar_init(cx.bar(B_EMPTY + i), 1); }
-  for (int i = 0; i < NA_ST; ++i) { mbar_init(cx.bar(A_FULL + i), full_cnt); mbar_init(cx.bar(A_EMPTY + i), 1); }
+  for (int i = 0; i < NB_ST; ++i) { mbar_init(cx.bar(B_FULL + i), 1); mbar_init(cx.bar(B_EMPTY + i), 1); }
+  for (int i = 0; i < NA_ST; ++i) { mbar_init(cx.bar(A_FULL + i), 1); mbar_init(cx.bar(A_EMPTY + i), 1); }
   mbar_init(cx.bar(X_READY), 1);
+  mbar_init(cx.bar(X_READY + 1), 1);
   mbar_init(cx.bar(NET_READY), 1);
   mbar_init(cx.bar(NET_READY + 1), 1);
   for (int i = 0; i < 8; ++i) { mbar_init(cx.bar(SX_READY + i), 4); mbar_init(cx.bar(H_READY + i), 4); }
@@ -540,13 +581,13 @@ __device__ __forceinline__ void setup_barriers(const Ctx& cx) {
 // =============================================================================================
 // Phase A
 // =============================================================================================
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phaseA_kernel(const Params p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phaseA_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Ctx cx;
   cx.smem = smem_u32(smem_raw);
   cx.bars = cx.smem + OFF_BARS;
   cx.rank = cluster_ctarank();
-  cx.err = &g_tc_err;
+  cx.err = p.err;
   for (int i = 0; i < 6; ++i) cx.w[i] = 0;
   const long long t_begin = clock64();
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + OFF_BARS + N_BARS * 8);
@@ -564,30 +605,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
   const int nsl = p.nks_z + p.nks_c;
 
   if (warp == 0) {
-    // ===================== producer =====================
-    if (lane == 0) {
+    // ===================== producer (whole warp, uniform control flow) =====================
+    {
       Ring ra, rb;
       ra.init(cx.bar(A_FULL), cx.bar(A_EMPTY), NA_ST);
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST);
+      const uint32_t wb = (uint32_t)(pair % W_REPLICAS) * p.replica_stride;
       for (int tile = pair; tile < p.tilesA; tile += npairs) {
-        const uint8_t* zt = p.zc + ((size_t)(tile * 2 + cx.rank) * nsl) * A_SLICE;
+        const size_t zt = ((size_t)(tile * 2 + cx.rank) * nsl) * A_SLICE;
         for (int s = 0; s < nsl; ++s) {
-          load_a(cx, ra, zt + (size_t)s * A_SLICE);
-          for (int nb = 0; nb < 2; ++nb) load_b(cx, rb, wchunk(p, p.off_g1[0], s, nb, cx.rank));
+          load_a(cx, ra, &p.tm_zc, zt + (size_t)s * A_SLICE);
+          for (int nb = 0; nb < 2; ++nb) load_b(cx, rb, &p.tm_w, wb + wchunk(p.off_g1[0], s, nb, cx.rank));
         }
         for (int b = 0; b < p.n_pre; ++b) {
           for (int nb = 0; nb < 2; ++nb)
-            for (int s = 0; s < DH / KS; ++s) load_b(cx, rb, wchunk(p, p.off_g2[b], s, nb, cx.rank));
+            for (int s = 0; s < DH / KS; ++s) load_b(cx, rb, &p.tm_w, wb + wchunk(p.off_g2[b], s, nb, cx.rank));
           if (b + 1 < p.n_pre)
             for (int s = 0; s < p.nks_z; ++s) {
-              load_a(cx, ra, zt + (size_t)s * A_SLICE);
-              for (int nb = 0; nb < 2; ++nb) load_b(cx, rb, wchunk(p, p.off_g1[b + 1], s, nb, cx.rank));
+              load_a(cx, ra, &p.tm_zc, zt + (size_t)s * A_SLICE);
+              for (int nb = 0; nb < 2; ++nb) load_b(cx, rb, &p.tm_w, wb + wchunk(p.off_g1[b + 1], s, nb, cx.rank));
             }
-          for (int s = 0; s < DH / KS; ++s)
-            for (int nb = 0; nb < 2; ++nb) load_b(cx, rb, wchunk(p, p.off_g3[b], s, nb, cx.rank));
+          for (int sh = 0; sh < 2; ++sh)  // same quartered order as gemm_fc1
+            for (int nb = 0; nb < 2; ++nb)
+              for (int s = sh * 4; s < sh * 4 + 4; ++s) load_b(cx, rb, &p.tm_w, wb + wchunk(p.off_g3[b], s, nb, cx.rank));
         }
       }
-      if (p.stats && cx.rank == 0) {
+      if (p.stats && cx.rank == 0 && lane == 0) {
         unsigned long long* st = p.stats + (size_t)pair * 16;
         st[6] = clock64() - t_begin;
         st[7] = cx.w[0];
@@ -596,8 +639,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader) / relay (peer): whole warp, uniform ==========
-    {
+    // ===================== MMA issuer: leader CTA only, whole warp, uniform control flow ======
+    if (cx.rank == 0) {
       Ring ra, rb;
       ra.init(cx.bar(A_FULL), cx.bar(A_EMPTY), NA_ST);
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST);
@@ -606,13 +649,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
       for (int tile = pair; tile < p.tilesA; tile += npairs, ++it) {
         const uint32_t xcol = (it & 1) ? 256u : 0u, netcol = 256u - xcol;
         gemm_from_ring(cx, ra, rb, nsl, xcol, true);
+        // The previous tile's pool must have consumed its X_READY completions before they are
+        // signalled again (a waiter that misses one completion of a 1-count mbarrier waits for
+        // ever), and it must have finished reading the old X before fc_0 reuses it as NET.
+        if (it > 0) twait(cx, 4, cx.bar(XP_DONE), (it - 1) & 1, 330);
         signal(cx, X_READY);
+        signal(cx, X_READY + 1);
         for (int b = 0; b < p.n_pre; ++b, ++use) {
-          if (b == 0 && it > 0 && cx.rank == 0) twait(cx, 4, cx.bar(XP_DONE), (it - 1) & 1, 330);
           gemm_fc0(cx, rb, netcol, use & 1);
           if (b + 1 < p.n_pre) gemm_from_ring(cx, ra, rb, p.nks_z, xcol, false);
           gemm_fc1(cx, rb, xcol, use & 1);
-          signal(cx, X_READY);
         }
       }
       if (p.stats && cx.rank == 0 && lane == 0) {
@@ -631,12 +677,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
     for (int tile = pair; tile < p.tilesA; tile += npairs, ++it) {
       const uint32_t xcol = (it & 1) ? 256u : 0u, netcol = 256u - xcol;
       for (int b = 0; b < p.n_pre; ++b) {
-        twait(cx, 0, cx.bar(X_READY), xph, 401);
+        long long t0 = 0;
+        for (int nb = 0; nb < 2; ++nb) {
+          twait(cx, 0, cx.bar(X_READY + nb), xph, 401 + nb * 1000 + (int)it * 10000 + warp * 1000000 + (int)cx.rank * 100000000);
+          tc_fence_after();
+          t0 = clock64();
+          epi_to_operand(cx, e, xcol, nb, biasA + (size_t)b * DH, OFF_SX, SX_READY);
+          cx.w[2] += clock64() - t0;
+        }
         xph ^= 1;
-        tc_fence_after();
-        long long t0 = clock64();
-        for (int nb = 0; nb < 2; ++nb) epi_to_operand(cx, e, xcol, nb, biasA + (size_t)b * DH, OFF_SX, SX_READY);
-        cx.w[2] += clock64() - t0;
         for (int nb = 0; nb < 2; ++nb) {
           twait(cx, 1, cx.bar(NET_READY + nb), nph, 402 + nb);
           tc_fence_after();
@@ -647,9 +696,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
         nph ^= 1;
       }
       // ---- view mean-pool of the residual stream -> pooled x (fp32) in phase-B tile order ----
-      twait(cx, 0, cx.bar(X_READY), xph, 405);
-      xph ^= 1;
-      tc_fence_after();
       const long long tp0 = clock64();
       int v;
       bool valid;
@@ -659,7 +705,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
       const float inv = 1.0f / (float)p.ns;
       const long long tb = gp >> 7;
       const int cb = (int)((gp >> 6) & 1), rb_ = (int)(gp & 63);
-      for (int nb = 0; nb < 2; ++nb)
+      for (int nb = 0; nb < 2; ++nb) {
+        twait(cx, 0, cx.bar(X_READY + nb), xph, 405 + nb * 1000 + (int)it * 10000 + warp * 1000000 + (int)cx.rank * 100000000 + (int)xph * 500000000);
+        tc_fence_after();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t r[32];
@@ -688,6 +736,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
             }
           }
         }
+      }
+      xph ^= 1;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(cx.bar(XP_DONE), 0);
@@ -708,13 +758,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
 // =============================================================================================
 // Phase B
 // =============================================================================================
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phaseB_kernel(const Params p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phaseB_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Ctx cx;
   cx.smem = smem_u32(smem_raw);
   cx.bars = cx.smem + OFF_BARS;
   cx.rank = cluster_ctarank();
-  cx.err = &g_tc_err;
+  cx.err = p.err;
   for (int i = 0; i < 6; ++i) cx.w[i] = 0;
   const long long t_begin = clock64();
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + OFF_BARS + N_BARS * 8);
@@ -739,20 +789,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
   const uint32_t xcol = 0, netcol = 256;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       Ring rb;
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST);
+      const uint32_t wb = (uint32_t)(pair % W_REPLICAS) * p.replica_stride;
       for (int tile = pair; tile < p.tilesB; tile += npairs)
         for (int j = 0; j < p.n_post; ++j) {
           const int b = p.n_pre + j;
           for (int nb = 0; nb < 2; ++nb)
-            for (int s = 0; s < DH / KS; ++s) load_b(cx, rb, wchunk(p, p.off_g2[b], s, nb, cx.rank));
-          for (int s = 0; s < DH / KS; ++s)
-            for (int nb = 0; nb < 2; ++nb) load_b(cx, rb, wchunk(p, p.off_g3[b], s, nb, cx.rank));
+            for (int s = 0; s < DH / KS; ++s) load_b(cx, rb, &p.tm_w, wb + wchunk(p.off_g2[b], s, nb, cx.rank));
+          for (int sh = 0; sh < 2; ++sh)  // same quartered order as gemm_fc1
+            for (int nb = 0; nb < 2; ++nb)
+              for (int s = sh * 4; s < sh * 4 + 4; ++s) load_b(cx, rb, &p.tm_w, wb + wchunk(p.off_g3[b], s, nb, cx.rank));
         }
     }
   } else if (warp == 1) {
-    {
+    if (cx.rank == 0) {
       Ring rb;
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST);
       uint32_t use = 0;
@@ -760,7 +812,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
         for (int j = 0; j < p.n_post; ++j, ++use) {
           gemm_fc0(cx, rb, netcol, use & 1);
           gemm_fc1(cx, rb, xcol, use & 1);
-          signal(cx, X_READY);
         }
     }
   } else if (warp >= 4) {
@@ -812,16 +863,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
           epi_to_operand(cx, e, netcol, nb, bias0 + (size_t)b * DH, OFF_H, H_READY);
         }
         nph ^= 1;
-        mbar_wait(cx.bar(X_READY), xph, cx.err, 501);
-        xph ^= 1;
-        tc_fence_after();
-        if (j + 1 < p.n_post)
-          for (int nb = 0; nb < 2; ++nb) epi_to_operand(cx, e, xcol, nb, biasB + (size_t)(j + 1) * DH, OFF_SX, SX_READY);
+        if (j + 1 < p.n_post) {
+          for (int nb = 0; nb < 2; ++nb) {
+            mbar_wait(cx.bar(X_READY + nb), xph, cx.err, 501);
+            tc_fence_after();
+            epi_to_operand(cx, e, xcol, nb, biasB + (size_t)(j + 1) * DH, OFF_SX, SX_READY);
+          }
+          xph ^= 1;
+        }
       }
       // ---- lin_out(relu(x)) + head ----
       const float* bO = biasB + (size_t)p.n_post * DH;
       float part[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int nb = 0; nb < 2; ++nb)
+      for (int nb = 0; nb < 2; ++nb) {
+        if (p.n_post > 0) {
+          mbar_wait(cx.bar(X_READY + nb), xph, cx.err, 505);
+          tc_fence_after();
+        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t r[32];
@@ -835,6 +893,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
             for (int o = 0; o < 4; ++o) part[o] = fmaf(x, s_wout[o * DH + f0 + i], part[o]);
           }
         }
+      }
+      if (p.n_post > 0) xph ^= 1;
       tc_fence_before();
 #pragma unroll
       for (int o = 0; o < 4; ++o) s_part[(o * 4 + e.h * 2 + e.cs) * 64 + e.row] = part[o];
@@ -888,6 +948,40 @@ static Plan make_plan(const Layout& L, int ns, long long P, void* ws, size_t ws_
   pl.err = a.take<int>(4);
   pl.total = a.off + 256;
   return pl;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// A linear byte range viewed as rows of 256 B (128 x u16); a box of `box_rows` rows is a contiguous
+// copy of box_rows*256 bytes, so the pre-packed operand images load exactly as laid out.
+static int encode_rows256(CUtensorMap* tm, const void* base, size_t bytes, int box_rows) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    PNR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !p) {
+      set_err("cuTensorMapEncodeTiled is not available in this driver");
+      return PNR_ERR_CUDA;
+    }
+    fn = (EncodeTiledFn)p;
+  }
+  PNR_CHECK_ARG(((uintptr_t)base & 15) == 0, "TMA source must be 16-byte aligned");
+  cuuint64_t rows = (cuuint64_t)((bytes + 255) / 256);
+  if (rows < (cuuint64_t)box_rows) rows = box_rows;
+  cuuint64_t dims[2] = {128, rows};
+  cuuint64_t strides[1] = {256};
+  cuuint32_t box[2] = {128, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_err("cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return PNR_ERR_CUDA;
+  }
+  return PNR_OK;
 }
 
 static int launch_cluster(void (*kern)(const Params), int pairs, const Params& p, cudaStream_t st) {
@@ -945,8 +1039,12 @@ static int run_phases(const pnr_mlp& m, const Layout& L, const Plan& pl, int ns,
   p.x3 = pl.x3;
   p.out = out;
   p.apply_head = head;
-  p.err = pl.err;
+  PNR_TRY(ensure_err_word());
+  p.err = g_err_dev;
   p.stats = g_stats_ptr;
+  p.replica_stride = (uint32_t)L.total;
+  PNR_TRY(encode_rows256(&p.tm_w, m.packed, L.total * W_REPLICAS, B_CHUNK / B_SPLIT / 256));
+  PNR_TRY(encode_rows256(&p.tm_zc, pl.zc, (size_t)pl.tilesA * 2 * pl.nsl * A_SLICE, A_SLICE / A_SPLIT / 256));
   {
     ProfScope ps(PROF_PHASE_A, 2.0 * mac_pre * (double)P * ns, 0.0, st);
     PNR_TRY(launch_cluster(mlp_phaseA_kernel, num_pairs(pl.tilesA), p, st));
@@ -959,13 +1057,16 @@ static int run_phases(const pnr_mlp& m, const Layout& L, const Plan& pl, int ns,
 }
 
 int tc_check(cudaStream_t st) {
-  PNR_CUDA(cudaStreamSynchronize(st));
-  int v = 0;
-  PNR_CUDA(cudaMemcpyFromSymbol(&v, g_tc_err, sizeof(int)));
+  cudaError_t e = cudaStreamSynchronize(st);
+  int v = g_err_host ? *(volatile int*)g_err_host : 0;
   if (v != 0) {
-    int zero = 0;
-    cudaMemcpyToSymbol(g_tc_err, &zero, sizeof(int));
-    set_err("tensor-core MLP pipeline: barrier wait timed out (tag %d)", v);
+    g_err_host[0] = 0;
+    set_err("tensor-core MLP pipeline: barrier wait timed out (tag %d)%s", v,
+            e != cudaSuccess ? "; the kernel trapped and the CUDA context is lost" : "");
+    return PNR_ERR_CUDA;
+  }
+  if (e != cudaSuccess) {
+    set_err("cudaStreamSynchronize -> %s", cudaGetErrorString(e));
     return PNR_ERR_CUDA;
   }
   return PNR_OK;
@@ -985,7 +1086,7 @@ int net_forward_tc(const pnr_scene& sc, const pnr_mlp& m, const float* xyz, cons
   PNR_UNSUPPORTED(sc.feat_dtype != PNR_BF16, "bf16 path needs a bf16-packed pyramid");
   for (int l = 0; l < sc.n_levels; ++l)
     PNR_UNSUPPORTED(sc.C[l] % 8 != 0 || sc.ch_off[l] % 8 != 0, "bf16 gather needs channel counts that are multiples of 8");
-  PNR_CHECK_ARG(m.packed_bytes >= make_layout(m).total, "mlp.packed image too small");
+  PNR_CHECK_ARG(m.packed_bytes >= make_layout(m).total * W_REPLICAS, "mlp.packed image too small");
   Layout L = make_layout(m);
   Plan pl = make_plan(L, sc.ns, P, ws, ws_bytes);
   if (pl.total > ws_bytes + 256 || !ws) {
@@ -1015,7 +1116,7 @@ int mlp_forward_tc_rows(const pnr_mlp& m, const float* zx, int SB, int NS, int P
   PNR_TRY(tc_supported(m));
   PNR_UNSUPPORTED(NS > 32, "more than 32 source views per object");
   Layout L = make_layout(m);
-  PNR_CHECK_ARG(m.packed_bytes >= L.total, "mlp.packed image too small");
+  PNR_CHECK_ARG(m.packed_bytes >= L.total * W_REPLICAS, "mlp.packed image too small");
   long long pts = (long long)SB * P;
   Plan pl = make_plan(L, NS, pts, ws, ws_bytes);
   if (pl.total > ws_bytes + 256 || !ws) {

@@ -72,14 +72,36 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Bounded wait: a protocol bug must never hang the GPU.  On timeout the barrier id is recorded in
 // *err (global) and the wait returns; the kernel then runs to completion with garbage results and
 // the host reports the failure.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int tag) {
   // try_wait itself suspends the thread for a hardware-bounded interval, so this loop does not
   // spin hot.  (Default .acquire.cta semantics on purpose: a cluster-scope acquire makes ptxas emit
   // CCTL.IVALL -- a full L1 invalidate -- after every probe, which dominated the first profile.)
-  for (uint32_t it = 0; it < (1u << 24); ++it) {
+  // Wall-clock bound: 1 s without progress records `tag` in *err; once *err is set every wait in the
+  // grid gives up immediately, so a protocol bug drains the kernel in about a second.
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0 = 0;
+  for (uint32_t it = 1;; ++it) {
     if (mbar_try_wait(bar, parity)) return;
+    if ((it & 255) == 0) {
+      if (err && *(volatile int*)err != 0) return;
+      unsigned long long now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 1000000000ull) {
+        // *err lives in mapped pinned host memory: the tag survives the trap (which is the loud,
+        // deterministic way out -- draining a half-synchronised tcgen05 pipeline is not safe)
+        if (err) {
+          atomicCAS(err, 0, tag);
+          __threadfence_system();
+        }
+        __trap();
+      }
+    }
   }
-  if (err) atomicCAS(err, 0, tag);
 }
 
 // ---- async proxy / bulk copy ---------------------------------------------------------------------
@@ -90,6 +112,20 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+
+// 2-D tiled TMA load issued by either CTA of a cta_group::2 pair: data lands in THIS CTA's shared
+// memory, the transaction bytes complete on the LEADER (even) CTA's mbarrier at the same offset
+// (bit 24 of a shared::cluster address selects the CTA of the pair).  SASS: UTMALDG.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_smem, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          dst_smem),
+      "l"(tmap), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 
 // ---- tcgen05 ------------------------------------------------------------------------------------
