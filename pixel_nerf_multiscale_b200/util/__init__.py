@@ -1,2 +1,2 @@
 from .util import *  # noqa: F401,F403
-from . import conf  # noqa: F401
+from . import args, conf  # noqa: F401
