@@ -115,6 +115,11 @@ class PixelNeRFNet(torch.nn.Module):
         self.c = c
         self.invalidate_scene()
 
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_scene_cache"], state["_workspace"] = {}, None  # caches of device pointers: never copied
+        return state
+
     def invalidate_scene(self):
         """Drop the packed feature pyramid / camera block (after encode() or after the caller
         replaces ``encoder.latent(s)``)."""

@@ -73,6 +73,12 @@ class ResnetFC(nn.Module):
         self.activation = nn.ReLU()
         self._native_cache = {}
 
+    def __getstate__(self):
+        # the native descriptors (ctypes structs with device pointers) are a cache: never copied/pickled
+        state = self.__dict__.copy()
+        state["_native_cache"] = {}
+        return state
+
     # ---- native operand bookkeeping -------------------------------------------------------
     def _fingerprint(self):
         return tuple((p.data_ptr(), p._version, str(p.device)) for p in self.parameters())
