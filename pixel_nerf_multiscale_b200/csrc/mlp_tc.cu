@@ -255,6 +255,65 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
   }
 }
 
+// select one of three registers without dynamic indexing (which would go through local memory)
+__device__ __forceinline__ float sel3(float a, float b, float c, int i) { return i == 0 ? a : (i == 1 ? b : c); }
+
+// Production variant of the positional code: same layout as code_entry() (features.cuh), hardware
+// sine (the rounding to bf16 hides its ~1e-4 error at |arg| <= 300) and constant-divisor index math.
+struct CodeCtx {
+  int dz, db, coded, d_in, use_code, include_input, use_xyz, normalize_z;
+  float freq_factor;
+};
+__device__ __forceinline__ float code_entry_fast(const CodeCtx& c, const PointCam& pc, int j) {
+  if (j >= c.d_in) return 0.f;
+  auto base = [&](int i) -> float {
+    if (i < c.dz) {
+      if (c.use_xyz) return c.normalize_z ? sel3(pc.xr[0], pc.xr[1], pc.xr[2], i) : sel3(pc.xc[0], pc.xc[1], pc.xc[2], i);
+      return c.normalize_z ? -pc.xr[2] : -pc.xc[2];
+    }
+    return sel3(pc.vd[0], pc.vd[1], pc.vd[2], i - c.dz);
+  };
+  if (j >= c.coded) return sel3(pc.vd[0], pc.vd[1], pc.vd[2], j - c.coded);
+  if (!c.use_code) return base(j);
+  if (c.include_input) {
+    if (j < c.db) return base(j);
+    j -= c.db;
+  }
+  int g;
+  switch (c.db) {  // constant divisors -> multiply-shift
+    case 1: g = j; break;
+    case 3: g = j / 3; break;
+    case 4: g = j / 4; break;
+    case 6: g = j / 6; break;
+    default: g = j / c.db; break;
+  }
+  const int i = j - g * c.db;
+  const float freq = c.freq_factor * (float)(1 << (g >> 1));
+  const float phase = (g & 1) ? 1.57079637050628662109375f : 0.f;
+  return __sinf(fmaf(base(i), freq, phase));
+}
+
+// bilinear taps without the normalise/unnormalise round trip (identical up to ~1e-5 texel)
+__device__ __forceinline__ Taps make_taps_fast(float u, float v, int H, int W, float kx, float ky) {
+  const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+  const float ix = fminf(fmaxf(u * kx, 0.f), wm1), iy = fminf(fmaxf(v * ky, 0.f), hm1);
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const int x0 = (int)x0f, y0 = (int)y0f;
+  const float fx1 = ix - x0f, fy1 = iy - y0f, fx0 = 1.f - fx1, fy0 = 1.f - fy1;
+  const bool xin = x0 + 1 <= W - 1, yin = y0 + 1 <= H - 1;
+  const int x1 = xin ? x0 + 1 : x0, y1 = yin ? y0 + 1 : y0;
+  Taps t;
+  t.o00 = y0 * W + x0;
+  t.o01 = y0 * W + x1;
+  t.o10 = y1 * W + x0;
+  t.o11 = y1 * W + x1;
+  t.w00 = fx0 * fy0;
+  t.w01 = xin ? fx1 * fy0 : 0.f;
+  t.w10 = yin ? fx0 * fy1 : 0.f;
+  t.w11 = (xin && yin) ? fx1 * fy1 : 0.f;
+  return t;
+}
+
 __global__ void __launch_bounds__(256)
 point_features_bf16_kernel(const pnr_scene sc, const float* __restrict__ xyz, const float* __restrict__ viewdirs,
                            const float* __restrict__ rays, const float* __restrict__ z, int K, long long P, int ppw,
@@ -274,47 +333,70 @@ point_features_bf16_kernel(const pnr_scene sc, const float* __restrict__ xyz, co
     return;
   }
   float X[3], D[3];
-  load_point(xyz, viewdirs, rays, z, K, gp, X, D);
+  if (rays != nullptr) {
+    const unsigned gpu = (unsigned)gp, r = gpu / (unsigned)K;  // a chunk never exceeds 2^31 points
+    const float4 ra = __ldg(reinterpret_cast<const float4*>(rays) + 2 * (size_t)r);
+    const float4 rb = __ldg(reinterpret_cast<const float4*>(rays) + 2 * (size_t)r + 1);
+    const float t = __ldg(z + gpu);
+    X[0] = ra.x + t * ra.w;  // o + z * d
+    X[1] = ra.y + t * rb.x;
+    X[2] = ra.z + t * rb.y;
+    D[0] = ra.w;
+    D[1] = rb.x;
+    D[2] = rb.y;
+  } else {
+    load_point(xyz, viewdirs, nullptr, nullptr, 0, gp, X, D);
+  }
   PointCam pc;
   camera_project(sc.cams + v * 16, X, D, pc);
-  for (int l = 0; l < sc.n_levels; ++l) {
+  // ---- latent: lanes stride over all 8-channel groups of all levels ----
+  const int G = sc.d_latent >> 3;
+  for (int g = lane; g < G; g += 32) {
+    int l = 0;
+    while (l + 1 < sc.n_levels && (g << 3) >= sc.ch_off[l + 1]) ++l;
     const int C = sc.C[l], H = sc.H[l], W = sc.W[l];
-    Taps t = make_taps(pc.u, pc.v, H, W, sc.kx[l], sc.ky[l]);
-    const __nv_bfloat16* f = (const __nv_bfloat16*)sc.level[l] + (size_t)v * H * W * C;
-    for (int g = lane; g < (C >> 3); g += 32) {
-      // 4 x 128-bit loads: 8 consecutive channels of each tap (NHWC -> a warp reads 512 B per tap)
-      uint4 q00 = __ldg(reinterpret_cast<const uint4*>(f + (size_t)t.o00 * C) + g);
-      uint4 q01 = __ldg(reinterpret_cast<const uint4*>(f + (size_t)t.o01 * C) + g);
-      uint4 q10 = __ldg(reinterpret_cast<const uint4*>(f + (size_t)t.o10 * C) + g);
-      uint4 q11 = __ldg(reinterpret_cast<const uint4*>(f + (size_t)t.o11 * C) + g);
-      float a[8], b[8], c[8], d[8];
-      bf16x8_to_float(q00, a);
-      bf16x8_to_float(q01, b);
-      bf16x8_to_float(q10, c);
-      bf16x8_to_float(q11, d);
-      uint32_t o[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float lo = a[2 * e] * t.w00 + b[2 * e] * t.w01 + c[2 * e] * t.w10 + d[2 * e] * t.w11;
-        float hi = a[2 * e + 1] * t.w00 + b[2 * e + 1] * t.w01 + c[2 * e + 1] * t.w10 + d[2 * e + 1] * t.w11;
-        o[e] = pack_bf16x2(lo, hi);
-      }
-      int kg = (sc.ch_off[l] >> 3) + g;
-      *reinterpret_cast<uint4*>(base + (size_t)kg * 1024) = make_uint4(o[0], o[1], o[2], o[3]);
-    }
-  }
-  // zero padding of the latent part (d_latent is a multiple of 64 on this path) is not needed;
-  // code part: nks_c slices, entries >= d_in are zero
-  for (int g = lane; g < nks_c * 8; g += 32) {
+    const Taps t = make_taps_fast(pc.u, pc.v, H, W, sc.kx[l], sc.ky[l]);
+    const int C8 = C >> 3, gl = g - (sc.ch_off[l] >> 3);
+    const uint4* f = reinterpret_cast<const uint4*>(sc.level[l]) + (size_t)v * H * W * C8 + gl;
+    // 4 x 128-bit loads: 8 consecutive channels of each tap (NHWC: a warp reads 512 contiguous B per tap)
+    const uint4 q00 = __ldg(f + (size_t)t.o00 * C8), q01 = __ldg(f + (size_t)t.o01 * C8);
+    const uint4 q10 = __ldg(f + (size_t)t.o10 * C8), q11 = __ldg(f + (size_t)t.o11 * C8);
+    float a[8], b[8], c[8], d[8];
+    bf16x8_to_float(q00, a);
+    bf16x8_to_float(q01, b);
+    bf16x8_to_float(q10, c);
+    bf16x8_to_float(q11, d);
     uint32_t o[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      int j = g * 8 + 2 * e;
-      float lo = j < sc.d_in ? code_entry(sc, pc, j) : 0.f;
-      float hi = j + 1 < sc.d_in ? code_entry(sc, pc, j + 1) : 0.f;
+      float lo = a[2 * e] * t.w00 + b[2 * e] * t.w01 + c[2 * e] * t.w10 + d[2 * e] * t.w11;
+      float hi = a[2 * e + 1] * t.w00 + b[2 * e + 1] * t.w01 + c[2 * e + 1] * t.w10 + d[2 * e + 1] * t.w11;
       o[e] = pack_bf16x2(lo, hi);
     }
-    *reinterpret_cast<uint4*>(base + (size_t)(nks_z * 8 + g) * 1024) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(base + (size_t)g * 1024) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  // ---- positional code: every lane evaluates entries lane, lane+32, ...; groups of 8 consecutive
+  //      entries are then collected into one lane by shuffles and stored as one 16-byte k-group ----
+  CodeCtx cc;
+  cc.dz = sc.use_xyz ? 3 : 1;
+  cc.db = cc.dz + ((sc.use_viewdirs && sc.use_code && sc.use_code_viewdirs) ? 3 : 0);
+  cc.coded = sc.use_code ? (sc.num_freqs * 2 * cc.db + (sc.include_input ? cc.db : 0)) : cc.db;
+  cc.d_in = sc.d_in;
+  cc.use_code = sc.use_code;
+  cc.include_input = sc.include_input;
+  cc.use_xyz = sc.use_xyz;
+  cc.normalize_z = sc.normalize_z;
+  cc.freq_factor = sc.freq_factor;
+  for (int t = 0; t < nks_c * 2; ++t) {  // 32 entries per pass -> 4 groups
+    const float e = code_entry_fast(cc, pc, t * 32 + lane);
+    float w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = __shfl_sync(0xffffffffu, e, ((lane & 3) << 3) + k);
+    if (lane < 4) {
+      const int g = t * 4 + lane;
+      *reinterpret_cast<uint4*>(base + (size_t)(nks_z * 8 + g) * 1024) =
+          make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]), pack_bf16x2(w[4], w[5]), pack_bf16x2(w[6], w[7]));
+    }
   }
 }
 
