@@ -16,6 +16,7 @@
 // The [latent|code] operand rows are produced by the bf16 variant of kernel (a) below
 // (128-bit gathers of the NHWC bf16 pyramid, written directly in UMMA panel order).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "features.cuh"
 #include "tc_ptx.cuh"
@@ -65,7 +66,7 @@ static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 // barrier indices (uint64 each)
 constexpr int B_FULL = 0, B_EMPTY = B_FULL + NB_ST, A_FULL = B_EMPTY + NB_ST, A_EMPTY = A_FULL + NA_ST,
               X_READY = A_EMPTY + NA_ST, NET_READY = X_READY + 2, SX_READY = NET_READY + 2, H_READY = SX_READY + 8,
-              XP_DONE = H_READY + 8, N_BARS = XP_DONE + 1;
+              XP_DONE = H_READY + 8, ZC_READY = XP_DONE + 1, ZC_TAKEN = ZC_READY + 1, N_BARS = ZC_TAKEN + 1;
 
 struct Params {
   const uint8_t* w;                    // packed image base
@@ -85,6 +86,11 @@ struct Params {
   int apply_head;
   int* err;
   unsigned long long* stats;           // optional [pairs][16] cycle counters (debug)
+  // in-kernel gather (warps 2-3 of phase A produce the operand image one tile ahead of the MMAs)
+  int fused_gather;                    // 0: zc was written by point_features_bf16_kernel
+  const float *xyz, *viewdirs, *rays, *zsamp;
+  int K;
+  pnr_scene sc;
   CUtensorMap tm_w;                    // packed weights as rows of 256 B, box = 16 rows (4 KB)
   CUtensorMap tm_zc;                   // operand image as rows of 256 B, box = 32 rows (8 KB)
 };
@@ -400,6 +406,80 @@ point_features_bf16_kernel(const pnr_scene sc, const float* __restrict__ xyz, co
   }
 }
 
+// Per-lane variant used by the gather warps inside phase A: lane = one row of the tile; the lane loops
+// over the 8-channel groups (4 scattered 128-bit tap loads each; adjacent groups share 32-B sectors
+// through L1) and over the code groups, and writes 16-byte operand entries -- a warp stores 512
+// contiguous bytes per group.
+__device__ __forceinline__ void gather_row_to_zc(const pnr_scene& sc, const float* __restrict__ xyz,
+                                                 const float* __restrict__ viewdirs, const float* __restrict__ rays,
+                                                 const float* __restrict__ z, int K, long long gp, int v, bool valid,
+                                                 int nks_z, int nks_c, uint8_t* __restrict__ base /* + kgroup*1024 */) {
+  const int nsl = nks_z + nks_c;
+  if (!valid) {
+    for (int g = 0; g < nsl * 8; ++g) *reinterpret_cast<uint4*>(base + (size_t)g * 1024) = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  float X[3], D[3];
+  if (rays != nullptr) {
+    const unsigned gpu = (unsigned)gp, r = gpu / (unsigned)K;
+    const float4 ra = __ldg(reinterpret_cast<const float4*>(rays) + 2 * (size_t)r);
+    const float4 rb = __ldg(reinterpret_cast<const float4*>(rays) + 2 * (size_t)r + 1);
+    const float t = __ldg(z + gpu);
+    X[0] = ra.x + t * ra.w;
+    X[1] = ra.y + t * rb.x;
+    X[2] = ra.z + t * rb.y;
+    D[0] = ra.w;
+    D[1] = rb.x;
+    D[2] = rb.y;
+  } else {
+    load_point(xyz, viewdirs, nullptr, nullptr, 0, gp, X, D);
+  }
+  PointCam pc;
+  camera_project(sc.cams + v * 16, X, D, pc);
+  for (int l = 0; l < sc.n_levels; ++l) {
+    const int C8 = sc.C[l] >> 3, H = sc.H[l], W = sc.W[l];
+    const Taps t = make_taps_fast(pc.u, pc.v, H, W, sc.kx[l], sc.ky[l]);
+    const uint4* f = reinterpret_cast<const uint4*>(sc.level[l]) + (size_t)v * H * W * C8;
+    const uint4 *p00 = f + (size_t)t.o00 * C8, *p01 = f + (size_t)t.o01 * C8, *p10 = f + (size_t)t.o10 * C8,
+                *p11 = f + (size_t)t.o11 * C8;
+    uint8_t* dst = base + (size_t)(sc.ch_off[l] >> 3) * 1024;
+#pragma unroll 4
+    for (int g = 0; g < C8; ++g) {
+      const uint4 q00 = __ldg(p00 + g), q01 = __ldg(p01 + g), q10 = __ldg(p10 + g), q11 = __ldg(p11 + g);
+      float a[8], b[8], c[8], d[8];
+      bf16x8_to_float(q00, a);
+      bf16x8_to_float(q01, b);
+      bf16x8_to_float(q10, c);
+      bf16x8_to_float(q11, d);
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float lo = a[2 * e] * t.w00 + b[2 * e] * t.w01 + c[2 * e] * t.w10 + d[2 * e] * t.w11;
+        float hi = a[2 * e + 1] * t.w00 + b[2 * e + 1] * t.w01 + c[2 * e + 1] * t.w10 + d[2 * e + 1] * t.w11;
+        o[e] = pack_bf16x2(lo, hi);
+      }
+      *reinterpret_cast<uint4*>(dst + (size_t)g * 1024) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  CodeCtx cc;
+  cc.dz = sc.use_xyz ? 3 : 1;
+  cc.db = cc.dz + ((sc.use_viewdirs && sc.use_code && sc.use_code_viewdirs) ? 3 : 0);
+  cc.coded = sc.use_code ? (sc.num_freqs * 2 * cc.db + (sc.include_input ? cc.db : 0)) : cc.db;
+  cc.d_in = sc.d_in;
+  cc.use_code = sc.use_code;
+  cc.include_input = sc.include_input;
+  cc.use_xyz = sc.use_xyz;
+  cc.normalize_z = sc.normalize_z;
+  cc.freq_factor = sc.freq_factor;
+  for (int g = 0; g < nks_c * 8; ++g) {
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      o[e] = pack_bf16x2(code_entry_fast(cc, pc, g * 8 + 2 * e), code_entry_fast(cc, pc, g * 8 + 2 * e + 1));
+    *reinterpret_cast<uint4*>(base + (size_t)(nks_z * 8 + g) * 1024) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // fp32 rows in reference order (sb, ns, p) -> operand image (used by pnr_mlp_forward in bf16 mode)
 __global__ void __launch_bounds__(256)
 rows_to_operand_kernel(const float* __restrict__ zx, int d_latent, int d_in, int SB, int NS, long long Pper, int ppw,
@@ -656,6 +736,8 @@ __device__ __forceinline__ void setup_barriers(const Ctx& cx) {
   mbar_init(cx.bar(NET_READY + 1), 1);
   for (int i = 0; i < 8; ++i) { mbar_init(cx.bar(SX_READY + i), 4); mbar_init(cx.bar(H_READY + i), 4); }
   mbar_init(cx.bar(XP_DONE), 16);
+  mbar_init(cx.bar(ZC_READY), 2);   // the two gather warps of THIS CTA
+  mbar_init(cx.bar(ZC_TAKEN), 1);   // this CTA's producer
   for (int i = 0; i < 2 * NB_ST; ++i) *ts_slot(i / NB_ST, i % NB_ST) = 0;
   fence_mbar_init();
 }
@@ -693,7 +775,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
       ra.init(cx.bar(A_FULL), cx.bar(A_EMPTY), NA_ST);
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST);
       const uint32_t wb = (uint32_t)(pair % W_REPLICAS) * p.replica_stride;
-      for (int tile = pair; tile < p.tilesA; tile += npairs) {
+      uint32_t git = 0;
+      for (int tile = pair; tile < p.tilesA; tile += npairs, ++git) {
+        if (p.fused_gather) {  // this CTA's rows of the tile have been gathered (and are visible to TMA)
+          twait(cx, 1, cx.bar(ZC_READY), git & 1, 203);
+          if (elect_one()) mbar_arrive(cx.bar(ZC_TAKEN));
+          __syncwarp();
+        }
         const size_t zt = ((size_t)(tile * 2 + cx.rank) * nsl) * A_SLICE;
         for (int s = 0; s < nsl; ++s) {
           load_a(cx, ra, &p.tm_zc, zt + (size_t)s * A_SLICE);
@@ -748,6 +836,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
         st[0] = clock64() - t_begin;
         for (int i = 0; i < 5; ++i) st[1 + i] = cx.w[i];
         p.stats[74 * 16 + pair] = cx.w[5];  // sum of issue -> full-observed latencies
+      }
+    }
+  } else if (warp < 4) {
+    // ===================== gather warps (2, 3): operand image of the NEXT tiles ==================
+    if (p.fused_gather) {
+      uint32_t git = 0;
+      for (int tile = pair; tile < p.tilesA; tile += npairs, ++git) {
+        const int row = (warp - 2) * 32 + lane;
+        int v;
+        bool valid;
+        long long gp = tileA_point(tile, (int)cx.rank, row, p.ns, p.ppw, v, valid);
+        valid = valid && gp < p.P;
+        uint8_t* base = const_cast<uint8_t*>(p.zc) + ((size_t)(tile * 2 + cx.rank) * nsl) * A_SLICE + (size_t)row * 16;
+        gather_row_to_zc(p.sc, p.xyz, p.viewdirs, p.rays, p.zsamp, p.K, gp, v, valid, p.nks_z, p.nks_c, base);
+        // generic-proxy global writes -> visible to the async proxy (TMA) of this SM before the signal
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        // Signal only after the producer has consumed the previous tile's signal: a 1-phase-deep
+        // mbarrier must never complete twice before its waiter looks (and this also keeps the
+        // gather at most ~one tile ahead, so the image is still in L2 when TMA reads it).
+        if (git >= 1) twait(cx, 2, cx.bar(ZC_TAKEN), (git - 1) & 1, 204);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(cx.bar(ZC_READY));
       }
     }
   } else if (warp >= 4) {
@@ -1091,8 +1202,14 @@ static int num_pairs(int tiles) {
   return tiles < pairs ? tiles : pairs;
 }
 
+struct GatherArgs {
+  const pnr_scene* sc;
+  const float *xyz, *viewdirs, *rays, *z;
+  int K;
+};
+
 static int run_phases(const pnr_mlp& m, const Layout& L, const Plan& pl, int ns, long long P, float* out, int head,
-                      cudaStream_t st) {
+                      cudaStream_t st, const GatherArgs* ga = nullptr) {
   // algorithmic work (2*MACs of the nn.Linear layers, unpadded)
   const double mac_pre = (double)m.d_in * DH + (double)L.n_pre * m.d_latent * DH + 2.0 * L.n_pre * DH * DH;
   const double mac_post = 2.0 * L.n_post * DH * DH + (double)DH * m.d_out;
@@ -1121,6 +1238,15 @@ static int run_phases(const pnr_mlp& m, const Layout& L, const Plan& pl, int ns,
   p.x3 = pl.x3;
   p.out = out;
   p.apply_head = head;
+  if (ga) {
+    p.fused_gather = 1;
+    p.sc = *ga->sc;
+    p.xyz = ga->xyz;
+    p.viewdirs = ga->viewdirs;
+    p.rays = ga->rays;
+    p.zsamp = ga->z;
+    p.K = ga->K;
+  }
   PNR_TRY(ensure_err_word());
   p.err = g_err_dev;
   p.stats = g_stats_ptr;
@@ -1176,6 +1302,14 @@ int net_forward_tc(const pnr_scene& sc, const pnr_mlp& m, const float* xyz, cons
     return PNR_ERR_WORKSPACE;
   }
   PNR_CUDA(cudaMemsetAsync(pl.err, 0, 16, st));
+  static const bool fused = [] {
+    const char* e = getenv("PNR_FUSED_GATHER");
+    return !(e && e[0] == '0');
+  }();
+  if (fused) {
+    GatherArgs ga{&sc, xyz, viewdirs, rays, z, K};
+    return run_phases(m, L, pl, sc.ns, P, out, 1, st, &ga);
+  }
   long long wrows = (long long)pl.tilesA * 128;
   {
     // algorithmic gather bytes: 4 taps x d_latent x 2 B per (point, view) + operand row written once
