@@ -333,6 +333,32 @@ def main():
             rate, sec = cpu_render_rate(scene, conf, all_rays[pick.to(device)].cpu(), 2, 1)
             cpu = {"value": rate, "unit": unit, "cores": torch.get_num_threads(), "kind": "port",
                    "sample": "%d-ray sample of %s, 2 timed calls after 1 warm-up, oracle (torch %s CPU)" % (sample, wl_name, torch.__version__)}
+        eager = None
+        if not args.no_cpu_baseline:
+            # honest software bar: the same oracle arithmetic as PyTorch eager ops on this
+            # B200 (fp32, TF32 off), bounded sample; reported only, never the measured arm
+            try:
+                from oracle import pixelnerf_oracle as po
+
+                torch.backends.cuda.matmul.allow_tf32 = False
+                gscene = oracle_scene(net, cam, conf, device=device)
+                sample = 8192
+                rs = all_rays[torch.randperm(all_rays.shape[0], generator=torch.Generator().manual_seed(3))[:sample].to(device)]
+                r = conf["renderer"]
+                kw = dict(n_coarse=r.get_int("n_coarse", 128), n_fine=r.get_int("n_fine", 0),
+                          n_fine_depth=r.get_int("n_fine_depth", 0), depth_std=r.get_float("depth_std", 0.01),
+                          white_bkgd=bool(r.get_float("white_bkgd", False)), lindisp=False, eval_batch_size=200000)
+                with torch.no_grad():
+                    po.render(gscene, rs[None, :1024], **kw)
+                    torch.cuda.synchronize(device)
+                    t0 = time.perf_counter()
+                    po.render(gscene, rs[None], **kw)
+                    torch.cuda.synchronize(device)
+                    dt = time.perf_counter() - t0
+                eager = {"value": sample / dt, "unit": unit, "sample": "%d rays, oracle ops on cuda (torch %s eager, fp32)" % (sample, torch.__version__)}
+                del gscene
+            except Exception as ex:  # pragma: no cover
+                eager = {"error": str(ex)[:200]}
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -341,7 +367,7 @@ def main():
                            "consecutive steps render different ray batches"),
             "points_per_sec": value * 160, "clocks": clocks,
             "e2e": {"value": e2e, "unit": unit, "h2d_bytes_per_step": B * 8 * 4, "d2h_bytes_per_step": B * 4 * 4},
-            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "torch_eager_gpu": eager}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
