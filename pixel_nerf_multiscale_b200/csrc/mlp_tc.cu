@@ -49,23 +49,24 @@ constexpr int ROWS = 64;                // rows per CTA
 constexpr int KS = 64;                  // K elements per slice
 constexpr int B_CHUNK = 128 * KS * 2;   // 16 KB: [8 k-groups][128 n-rows][8 bf16]
 constexpr int A_SLICE = ROWS * KS * 2;  // 8 KB : [8 k-groups][64 rows][8 bf16]
-constexpr int NB_ST = 5, NA_ST = 2;
+constexpr int NB_ST = 6;                // unified operand ring: weight chunks (16 KB) and [latent|code] slices (8 KB)
+constexpr int NB_ST_B = 5;              // phase B: 5 slots, the 6th holds the lin_out weights / partial sums
 constexpr int B_SPLIT = 8;              // TMA boxes per weight chunk (2 KB each: small boxes land sooner)
 constexpr int A_SPLIT = 4;              // TMA boxes per operand slice
-constexpr int W_REPLICAS = 4;           // copies of the packed weights; pair p streams copy p % W_REPLICAS so that
-                                        // 74 pairs do not all hit the same L2 lines at the same time
+constexpr int W_REPLICAS = 1;           // copies of the packed weights; pair p streams copy p % W_REPLICAS so that
+                                        // 74 pairs do not all hit the same L2 lines at the same time (measured: no effect -> 1)
 constexpr int OFF_SX = 0;
 constexpr int OFF_H = OFF_SX + ROWS * DH * 2;
 constexpr int OFF_BRING = OFF_H + ROWS * DH * 2;
-constexpr int OFF_ARING = OFF_BRING + NB_ST * B_CHUNK;
-constexpr int OFF_BARS = OFF_ARING + NA_ST * A_SLICE;
+constexpr int OFF_LINOUT = OFF_BRING + NB_ST_B * B_CHUNK;
+constexpr int OFF_BARS = OFF_BRING + NB_ST * B_CHUNK;
 constexpr int SMEM_BYTES = OFF_BARS + 512;
 constexpr int THREADS = 384;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
 // barrier indices (uint64 each)
-constexpr int B_FULL = 0, B_EMPTY = B_FULL + NB_ST, A_FULL = B_EMPTY + NB_ST, A_EMPTY = A_FULL + NA_ST,
-              X_READY = A_EMPTY + NA_ST, NET_READY = X_READY + 2, SX_READY = NET_READY + 2, H_READY = SX_READY + 8,
+constexpr int B_FULL = 0, B_EMPTY = B_FULL + NB_ST,
+              X_READY = B_EMPTY + NB_ST, NET_READY = X_READY + 2, SX_READY = NET_READY + 2, H_READY = SX_READY + 8,
               XP_DONE = H_READY + 8, ZC_READY = XP_DONE + 1, ZC_TAKEN = ZC_READY + 1, N_BARS = ZC_TAKEN + 1;
 
 struct Params {
@@ -76,7 +77,7 @@ struct Params {
   uint32_t off_biasA, off_biasB, off_bias0, off_lin_out;  // fp32 tables
   int n_pre, n_post;                   // blocks before / after the view pool
   int nks_z, nks_c;                    // K slices of the latent / code part of an input row
-  int ns, ppw;                         // views per point, points per 32-row group
+  int ns, ppw;                         // views per point, points per CTA (= 64 / ns; rows pl*ns + v)
   long long P;                         // points
   int tilesA, tilesB;
   uint32_t replica_stride;             // bytes between weight replicas
@@ -98,15 +99,15 @@ struct Params {
 using namespace tc;
 
 // ---------------------------------------------------------------------------------------------
-// row <-> point mapping of a phase-A tile: CTA c, row r: group rg=r/32, rr=r%32, point-in-group
-// pl=rr/ns, view v=rr%ns (rows with pl>=ppw are padding)
+// row <-> point mapping of a phase-A tile: CTA c, row r (0..63): point-in-CTA pl = r / ns, view
+// v = r % ns; rows with pl >= ppc (= 64 / ns) are padding.  A point's rows are adjacent TMEM lanes; for
+// ns that do not divide 32 one point straddles the two 32-lane groups (handled in the pool epilogue).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ long long tileA_point(int tile, int cta, int row, int ns, int ppw, int& v, bool& valid) {
-  int rg = row >> 5, rr = row & 31;
-  int pl = rr / ns;
-  v = rr - pl * ns;
-  valid = pl < ppw;
-  return ((long long)(tile * 2 + cta) * 2 + rg) * ppw + pl;
+__device__ __forceinline__ long long tileA_point(int tile, int cta, int row, int ns, int ppc, int& v, bool& valid) {
+  int pl = row / ns;
+  v = row - pl * ns;
+  valid = pl < ppc;
+  return (long long)(tile * 2 + cta) * ppc + pl;
 }
 
 // =============================================================================================
@@ -582,7 +583,7 @@ __device__ __forceinline__ void load_b(Ctx& cx, Ring& rb, const CUtensorMap* tm,
 }
 __device__ __forceinline__ void load_a(Ctx& cx, Ring& ra, const CUtensorMap* tm, size_t byte_off) {
   twait(cx, 1, ra.empty_bar(), ra.phase ^ 1, 202);
-  const uint32_t dst = cx.smem + OFF_ARING + ra.idx * A_SLICE, fb = ra.full_bar();
+  const uint32_t dst = cx.smem + OFF_BRING + ra.idx * B_CHUNK, fb = ra.full_bar();  // an 8 KB slice in a 16 KB slot
   if (elect_one()) {
     if (cx.rank == 0) mbar_expect_tx(fb, 2 * A_SLICE);
 #pragma unroll
@@ -631,28 +632,22 @@ __device__ __forceinline__ void mma_step_b(Ctx& cx, Ring& rb, uint32_t a_addr, u
   }
   rb.advance();
 }
-__device__ __forceinline__ void a_wait(Ctx& cx, Ring& ra) { twait(cx, 1, ra.full_bar(), ra.phase, 302); }
-__device__ __forceinline__ void a_release(const Ctx& cx, Ring& ra) {
-  if (cx.rank == 0) {
-    if (elect_one()) mma_commit<2>(ra.empty_bar(), 0x3);
-    __syncwarp();
-  }
-  ra.advance();
-}
 __device__ __forceinline__ void signal(const Ctx& cx, int bar_idx) {
-  if (cx.rank == 0) {
-    if (elect_one()) mma_commit<2>(cx.bar(bar_idx), 0x3);
-    __syncwarp();
-  }
+  if (elect_one()) mma_commit<2>(cx.bar(bar_idx), 0x3);
+  __syncwarp();
 }
 
-// x[:, all 512] (+)= A_ring @ W^T over `nks` slices (k-outer).  first_acc0: overwrite on slice 0.
-__device__ __forceinline__ void gemm_from_ring(Ctx& cx, Ring& ra, Ring& rb, int nks, uint32_t xcol, bool overwrite) {
+// x[:, all 512] (+)= A @ W^T over `nks` slices (k-outer) with A streamed through the ring: per slice the
+// ring carries [A slice][W block 0][W block 1]; the A slot is released after both column blocks.
+__device__ __forceinline__ void gemm_from_ring(Ctx& cx, Ring& rb, int nks, uint32_t xcol, bool overwrite) {
   for (int s = 0; s < nks; ++s) {
-    a_wait(cx, ra);
-    uint32_t a_addr = cx.smem + OFF_ARING + ra.idx * A_SLICE;
+    twait(cx, 1, rb.full_bar(), rb.phase, 302);
+    const uint32_t a_addr = cx.smem + OFF_BRING + rb.idx * B_CHUNK;
+    const uint32_t a_empty = rb.empty_bar();
+    rb.advance();
     for (int nb = 0; nb < 2; ++nb) mma_step_b(cx, rb, a_addr, xcol + nb * 128, overwrite && s == 0);
-    a_release(cx, ra);
+    if (elect_one()) mma_commit<2>(a_empty, 0x3);
+    __syncwarp();
   }
 }
 // NET = S_x @ W0^T, n-outer; waits for operand slices as the epilogue publishes them
@@ -729,7 +724,6 @@ __device__ __forceinline__ void epi_to_operand(const Ctx& cx, const Epi& e, uint
 
 __device__ __forceinline__ void setup_barriers(const Ctx& cx) {
   for (int i = 0; i < NB_ST; ++i) { mbar_init(cx.bar(B_FULL + i), 1); mbar_init(cx.bar(B_EMPTY + i), 1); }
-  for (int i = 0; i < NA_ST; ++i) { mbar_init(cx.bar(A_FULL + i), 1); mbar_init(cx.bar(A_EMPTY + i), 1); }
   mbar_init(cx.bar(X_READY), 1);
   mbar_init(cx.bar(X_READY + 1), 1);
   mbar_init(cx.bar(NET_READY), 1);
@@ -771,8 +765,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
   if (warp == 0) {
     // ===================== producer (whole warp, uniform control flow) =====================
     {
-      Ring ra, rb;
-      ra.init(cx.bar(A_FULL), cx.bar(A_EMPTY), NA_ST);
+      Ring rb;
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST);
       const uint32_t wb = (uint32_t)(pair % W_REPLICAS) * p.replica_stride;
       uint32_t git = 0;
@@ -784,7 +777,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
         }
         const size_t zt = ((size_t)(tile * 2 + cx.rank) * nsl) * A_SLICE;
         for (int s = 0; s < nsl; ++s) {
-          load_a(cx, ra, &p.tm_zc, zt + (size_t)s * A_SLICE);
+          load_a(cx, rb, &p.tm_zc, zt + (size_t)s * A_SLICE);
           for (int nb = 0; nb < 2; ++nb) load_b(cx, rb, &p.tm_w, wb + wchunk(p.off_g1[0], s, nb, cx.rank));
         }
         for (int b = 0; b < p.n_pre; ++b) {
@@ -792,7 +785,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
             for (int s = 0; s < DH / KS; ++s) load_b(cx, rb, &p.tm_w, wb + wchunk(p.off_g2[b], s, nb, cx.rank));
           if (b + 1 < p.n_pre)
             for (int s = 0; s < p.nks_z; ++s) {
-              load_a(cx, ra, &p.tm_zc, zt + (size_t)s * A_SLICE);
+              load_a(cx, rb, &p.tm_zc, zt + (size_t)s * A_SLICE);
               for (int nb = 0; nb < 2; ++nb) load_b(cx, rb, &p.tm_w, wb + wchunk(p.off_g1[b + 1], s, nb, cx.rank));
             }
           for (int sh = 0; sh < 2; ++sh)  // same quartered order as gemm_fc1
@@ -811,14 +804,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
   } else if (warp == 1) {
     // ===================== MMA issuer: leader CTA only, whole warp, uniform control flow ======
     if (cx.rank == 0) {
-      Ring ra, rb;
-      ra.init(cx.bar(A_FULL), cx.bar(A_EMPTY), NA_ST);
+      Ring rb;
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST);
       uint32_t use = 0;  // (tile-local block counter) parity source for SX/H barriers
       uint32_t it = 0;
       for (int tile = pair; tile < p.tilesA; tile += npairs, ++it) {
         const uint32_t xcol = (it & 1) ? 256u : 0u, netcol = 256u - xcol;
-        gemm_from_ring(cx, ra, rb, nsl, xcol, true);
+        gemm_from_ring(cx, rb, nsl, xcol, true);
         // The previous tile's pool must have consumed its X_READY completions before they are
         // signalled again (a waiter that misses one completion of a 1-count mbarrier waits for
         // ever), and it must have finished reading the old X before fc_0 reuses it as NET.
@@ -827,7 +819,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
         signal(cx, X_READY + 1);
         for (int b = 0; b < p.n_pre; ++b, ++use) {
           gemm_fc0(cx, rb, netcol, use & 1);
-          if (b + 1 < p.n_pre) gemm_from_ring(cx, ra, rb, p.nks_z, xcol, false);
+          if (b + 1 < p.n_pre) gemm_from_ring(cx, rb, p.nks_z, xcol, false);
           gemm_fc1(cx, rb, xcol, use & 1);
         }
       }
@@ -898,14 +890,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
       const float inv = 1.0f / (float)p.ns;
       const long long tb = gp >> 7;
       const int cb = (int)((gp >> 6) & 1), rb_ = (int)(gp & 63);
+      // A point whose NS rows straddle lanes 31|32 (NS not a divisor of 32) has its first `rem` rows in
+      // the lower warp and the other NS-rem in the partner warp (same columns, next TMEM quadrant):
+      // the upper warp pre-sums its rows and hands one value per column over through the idle S_x.
+      const int rem = 32 % p.ns, nup = p.ns - rem;
+      const bool straddle = rem != 0;
+      const bool upper = (e.q & 1) != 0;
+      const bool in1 = lane + 1 <= 31, in2 = lane + 2 <= 31;
+      const bool takes_spill = straddle && !upper && lane == 32 - rem;
+      const int pair_id = e.h * 2 + e.cs;                 // warps (q even, q odd) with equal h, cs
+      float4* spill = reinterpret_cast<float4*>(smem_raw + OFF_SX) + (size_t)pair_id * (2 * 2 * 8);
       for (int nb = 0; nb < 2; ++nb) {
-        twait(cx, 0, cx.bar(X_READY + nb), xph, 405 + nb * 1000 + (int)it * 10000 + warp * 1000000 + (int)cx.rank * 100000000 + (int)xph * 500000000);
+        twait(cx, 0, cx.bar(X_READY + nb), xph, 405 + nb * 1000 + (int)it * 10000 + warp * 1000000);
         tc_fence_after();
+        const long long tq0 = clock64();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t r[32];
           tmem_ld32(cx.tmem + e.lane_addr + xcol + nb * 128 + e.cs * 64 + half * 32, r);
           tmem_ld_wait();
+          float4* sp = spill + (nb * 2 + half) * 8;  // 32 columns
+          if (straddle) {
+            if (upper) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float u[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float x = __uint_as_float(r[4 * j + i]);
+                  float a = __shfl_sync(0xffffffffu, x, 0);
+                  for (int k = 1; k < nup; ++k) a += __shfl_sync(0xffffffffu, x, k);
+                  u[i] = a;
+                }
+                if (lane == 0) sp[j] = make_float4(u[0], u[1], u[2], u[3]);
+              }
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + pair_id) : "memory");
+          }
           const int f0 = feat0(e, nb, half);
           // x3[tileB][ctaB][nb][h][jq (32)][row (64)][4]
           float4* dst = reinterpret_cast<float4*>(p.x3) +
@@ -916,25 +937,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
             float s4[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              float x = __uint_as_float(r[4 * j + i]);
+              const float x = __uint_as_float(r[4 * j + i]);
               float s = x;
-              if (p.ns > 1) s += __shfl_down_sync(0xffffffffu, x, 1);
-              if (p.ns > 2) s += __shfl_down_sync(0xffffffffu, x, 2);
-              for (int k = 3; k < p.ns; ++k) s += __shfl_down_sync(0xffffffffu, x, k);
-              s4[i] = s * inv;
+              if (p.ns > 1) { float y = __shfl_down_sync(0xffffffffu, x, 1); s += in1 ? y : 0.f; }
+              if (p.ns > 2) { float y = __shfl_down_sync(0xffffffffu, x, 2); s += in2 ? y : 0.f; }
+              for (int k = 3; k < p.ns; ++k) { float y = __shfl_down_sync(0xffffffffu, x, k); s += (lane + k <= 31) ? y : 0.f; }
+              s4[i] = s;
+            }
+            if (takes_spill) {
+              const float4 u = sp[j];
+              s4[0] += u.x; s4[1] += u.y; s4[2] += u.z; s4[3] += u.w;
             }
             if (valid) {
-              float4 bb = __ldg(b4 + j);
-              dst[(size_t)j * 64] = make_float4(s4[0] + bb.x, s4[1] + bb.y, s4[2] + bb.z, s4[3] + bb.w);
+              const float4 bb = __ldg(b4 + j);
+              dst[(size_t)j * 64] = make_float4(s4[0] * inv + bb.x, s4[1] * inv + bb.y, s4[2] * inv + bb.z, s4[3] * inv + bb.w);
             }
           }
         }
+        cx.w[4] += clock64() - tq0;  // pool work only (waits excluded)
       }
       xph ^= 1;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(cx.bar(XP_DONE), 0);
-      cx.w[4] += clock64() - tp0;
+      (void)tp0;
     }
     if (p.stats && cx.rank == 0 && warp == 4 && lane == 0) {
       unsigned long long* st = p.stats + (size_t)pair * 16;
@@ -961,7 +987,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
   for (int i = 0; i < 6; ++i) cx.w[i] = 0;
   const long long t_begin = clock64();
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + OFF_BARS + N_BARS * 8);
-  float* s_wout = reinterpret_cast<float*>(smem_raw + OFF_ARING);          // [4][512] + [4]
+  float* s_wout = reinterpret_cast<float*>(smem_raw + OFF_LINOUT);          // [4][512] + [4]
   float* s_part = s_wout + 4 * DH + 4;                                    // [4 outputs][4 parts][64 rows]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) setup_barriers(cx);
@@ -984,7 +1010,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
   if (warp == 0) {
     {
       Ring rb;
-      rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST);
+      rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST_B);
       const uint32_t wb = (uint32_t)(pair % W_REPLICAS) * p.replica_stride;
       for (int tile = pair; tile < p.tilesB; tile += npairs)
         for (int j = 0; j < p.n_post; ++j) {
@@ -999,7 +1025,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
   } else if (warp == 1) {
     if (cx.rank == 0) {
       Ring rb;
-      rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST);
+      rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST_B);
       uint32_t use = 0;
       for (int tile = pair; tile < p.tilesB; tile += npairs)
         for (int j = 0; j < p.n_post; ++j, ++use) {
@@ -1130,8 +1156,8 @@ struct Plan {
 
 static Plan make_plan(const Layout& L, int ns, long long P, void* ws, size_t ws_bytes) {
   Plan pl;
-  pl.ppw = 32 / ns;
-  pl.ptile = 4 * pl.ppw;
+  pl.ppw = 64 / ns;
+  pl.ptile = 2 * pl.ppw;
   pl.tilesA = (int)ceil_div_ll(P, pl.ptile);
   pl.tilesB = (int)ceil_div_ll(P, 128);
   pl.nsl = L.nks_z + L.nks_c;
