@@ -12,8 +12,9 @@ SURVEY.md section 8d -- there is no dataset and no checkpoint):
     c2  SRN   128x128 2 source views  conf/exp/srn.conf   (single-scale, L=256)     [default, N=1]
     c3  DTU   300x400 3 source views  conf/exp/dtu.conf   (single-scale, L=256)
     c4  DTU   300x400 3 source views  dtu.conf + encoder.use_multi_scale (pyramid, L=512)
-Source images are random, the ResNet34 encoder is random-init (eval mode), the two ResnetFC MLPs are
-re-randomised (at default init every block is the identity).
+Source images are random, the ResNet34 encoder is random-init (eval mode; each feature level rescaled
+to unit RMS, as a trained encoder would emit), the two ResnetFC MLPs are re-randomised (at default
+init every block is the identity).
 
 Printed JSON (one line, rank 0): value = whole-job rays/s with rays resident in HBM; e2e = the same
 through the public API with rays in pinned host memory and rgb/depth read back every step;
@@ -84,6 +85,12 @@ def build_scene(wl, device, precision):
     c = None if wl["c"] is None else torch.tensor(wl["c"], dtype=torch.float32)[None]
     with torch.no_grad():
         net.encode(images, poses, focal.to(device), c=None if c is None else c.to(device))
+        # A random-init ResNet34 in eval mode has identity BatchNorm, so its activations grow ~10x per
+        # stage (std 0.1 -> 30); a trained encoder emits O(1) features.  Rescale every level to unit RMS
+        # so the synthetic scene has non-degenerate density (otherwise sigma saturates to 0 or huge).
+        for m in net.encoder.level_maps():
+            m.div_(m.pow(2).mean().sqrt().clamp_min(1e-6))
+        net.invalidate_scene()
     renderer = pk.NeRFRenderer.from_conf(conf["renderer"], lindisp=False, eval_batch_size=wl["rays"])
     return net, renderer, conf, dict(poses=poses, focal=focal, c=c)
 
