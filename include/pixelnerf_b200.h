@@ -155,6 +155,18 @@ size_t pnr_mlp_forward_workspace(const pnr_mlp* mlp, int SB, int NS, int P, int 
 int pnr_mlp_forward(const pnr_mlp* mlp, const float* zx, int SB, int NS, int P, int precision,
                     float* out, void* workspace, size_t workspace_bytes, pnr_stream stream);
 
+/* ---- ray generation ("next" row 1) ------------------------------------------ */
+/* util.gen_rays + unproj_map (src/util/util.py:118-148,243-281), ndc=False: N camera-to-world poses
+ * (N,4,4) row-major -> rays (N,H,W,8) = [origin, unit direction, near, far], generated on the device. */
+int pnr_gen_rays(const float* poses_c2w, int N, int W, int H, float fx, float fy, float cx, float cy,
+                 float z_near, float z_far, float* rays, pnr_stream stream);
+
+/* ---- output side ("next" row 3) ---------------------------------------------- */
+/* n floats of rendered rgb: v = clamp(rgb,0,1); u8 (nullable) = trunc(v*255) (eval/gen_video.py:226);
+ * *sse (nullable, fp64, caller-zeroed) += sum (v-gt)^2 for PSNR = -10 log10(sse/n) (eval/eval.py:278-300,
+ * src/util/util.py:479-486) without the per-batch .cpu() sync of the reference. */
+int pnr_finalize_rgb(const float* rgb, const float* gt, int64_t n, uint8_t* u8, double* sse, pnr_stream stream);
+
 /* ---- kernel (c): per-ray sampling / compositing (src/render/nerf.py) ------------------ */
 /* sample_coarse, nerf.py:98-118.  rays (B,8), jitter (B,Kc) -> z (B,Kc).                 */
 int pnr_sample_coarse(const float* rays, const float* jitter, int B, int Kc, int lindisp,

@@ -282,6 +282,20 @@ size_t pnr_mlp_forward_workspace(const pnr_mlp* mlp, int SB, int NS, int P, int 
   return mlp_tc_rows_workspace(*mlp, SB, NS, P) + 1024;
 }
 
+int pnr_gen_rays(const float* poses_c2w, int N, int W, int H, float fx, float fy, float cx, float cy, float z_near,
+                 float z_far, float* rays, pnr_stream stream) {
+  PNR_CHECK_ARG(poses_c2w && rays, "gen_rays: NULL pointer");
+  PNR_CHECK_ARG(N >= 0 && W > 0 && H > 0 && fx != 0.f && fy != 0.f, "gen_rays: bad camera");
+  PNR_CHECK_ARG(((uintptr_t)rays & 15) == 0, "gen_rays: rays must be 16-byte aligned");
+  return launch_gen_rays(poses_c2w, N, W, H, fx, fy, cx, cy, z_near, z_far, rays, (cudaStream_t)stream);
+}
+
+int pnr_finalize_rgb(const float* rgb, const float* gt, int64_t n, uint8_t* u8, double* sse, pnr_stream stream) {
+  PNR_CHECK_ARG(rgb != nullptr && n >= 0, "finalize_rgb: bad arguments");
+  PNR_CHECK_ARG(!(gt && !sse), "finalize_rgb: gt given without an sse accumulator");
+  return launch_finalize_rgb(rgb, gt, n, u8, sse, (cudaStream_t)stream);
+}
+
 int pnr_sample_coarse(const float* rays, const float* jitter, int B, int Kc, int lindisp, float* z, pnr_stream stream) {
   PNR_CHECK_ARG(rays && jitter && z, "sample_coarse: NULL pointer");
   PNR_CHECK_ARG(Kc >= 1, "sample_coarse: Kc must be >= 1");

@@ -99,6 +99,9 @@ int mlp_forward_f32(const pnr_mlp& m, const float* zx, int SB, int NS, int P, fl
 // rays.cu
 int launch_sample_coarse(const float* rays, const float* jitter, int B, int Kc, int lindisp, float* z,
                          cudaStream_t st);
+int launch_gen_rays(const float* poses, int N, int W, int H, float fx, float fy, float cx, float cy, float near,
+                    float far, float* rays, cudaStream_t st);
+int launch_finalize_rgb(const float* rgb, const float* gt, long long n, uint8_t* u8, double* sse, cudaStream_t st);
 int launch_composite(const float* rays, const float* z, const float* rgb_sigma, int B, int K, int white,
                      float* weights, float* rgb, float* depth, cudaStream_t st);
 int launch_fine_indices(const float* cdf, const float* u, int B, int Kc, int Kf, float* inds, cudaStream_t st);

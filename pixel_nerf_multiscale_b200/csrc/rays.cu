@@ -45,6 +45,76 @@ int launch_sample_coarse(const float* rays, const float* jitter, int B, int Kc, 
   return PNR_OK;
 }
 
+// ---- gen_rays: rays of N pinhole cameras, src/util/util.py:118-148,243-281 ----------
+// unproj = normalize((x-cx)/fx, -(y-cy)/fy, -1); dir = R * unproj; origin = t; near/far constants.
+__global__ void gen_rays_kernel(const float* __restrict__ poses, int N, int W, int H, float fx, float fy, float cx,
+                                float cy, float near, float far, float* __restrict__ rays) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)N * H * W;
+  if (i >= total) return;
+  int x = (int)(i % W);
+  long long t = i / W;
+  int y = (int)(t % H);
+  int n = (int)(t / H);
+  const float* P = poses + (size_t)n * 16;
+  float X = __fdiv_rn(__fsub_rn((float)x, cx), fx);
+  float Y = -__fdiv_rn(__fsub_rn((float)y, cy), fy);
+  float Z = -1.f;
+  float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(X, X), __fmul_rn(Y, Y)), 1.f));
+  X = __fdiv_rn(X, nrm);
+  Y = __fdiv_rn(Y, nrm);
+  Z = __fdiv_rn(Z, nrm);
+  float4 a, b;
+  a.x = P[3];
+  a.y = P[7];
+  a.z = P[11];
+  a.w = P[0] * X + P[1] * Y + P[2] * Z;
+  b.x = P[4] * X + P[5] * Y + P[6] * Z;
+  b.y = P[8] * X + P[9] * Y + P[10] * Z;
+  b.z = near;
+  b.w = far;
+  reinterpret_cast<float4*>(rays)[2 * i] = a;
+  reinterpret_cast<float4*>(rays)[2 * i + 1] = b;
+}
+
+int launch_gen_rays(const float* poses, int N, int W, int H, float fx, float fy, float cx, float cy, float near,
+                    float far, float* rays, cudaStream_t st) {
+  long long total = (long long)N * H * W;
+  if (total == 0) return PNR_OK;
+  gen_rays_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(poses, N, W, H, fx, fy, cx, cy, near, far, rays);
+  PNR_LAUNCHED();
+  return PNR_OK;
+}
+
+// ---- output side: clamp + uint8 quantisation + squared-error accumulation on device ---
+// u8 = trunc(clamp(rgb,0,1)*255) as eval/gen_video.py:226 does with numpy; sse += (clamp(rgb)-gt)^2 in fp64
+// (eval/eval.py:278-300 computes PSNR from the clamped image), no host synchronisation.
+__global__ void finalize_rgb_kernel(const float* __restrict__ rgb, const float* __restrict__ gt, long long n,
+                                    uint8_t* __restrict__ u8, double* __restrict__ sse) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double e = 0.0;
+  if (i < n) {
+    float v = fminf(fmaxf(rgb[i], 0.f), 1.f);
+    if (u8) u8[i] = (uint8_t)(v * 255.f);
+    if (gt) {
+      float d = v - gt[i];
+      e = (double)d * (double)d;
+    }
+  }
+  if (sse) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    if ((threadIdx.x & 31) == 0 && e != 0.0) atomicAdd(sse, e);
+  }
+}
+
+int launch_finalize_rgb(const float* rgb, const float* gt, long long n, uint8_t* u8, double* sse, cudaStream_t st) {
+  if (n == 0) return PNR_OK;
+  finalize_rgb_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(rgb, gt, n, u8, sse);
+  PNR_LAUNCHED();
+  return PNR_OK;
+}
+
 // ---- composite --------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

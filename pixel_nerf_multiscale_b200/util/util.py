@@ -52,6 +52,22 @@ def gen_rays(poses, width, height, focal, z_near, z_far, c=None, ndc=False):
         raise NotImplementedError("ndc rays (undefined in the reference as well: util.py:265)")
     n = poses.shape[0]
     dev = poses.device
+    if poses.is_cuda:  # generated on the device by the native library (no (N,H,W,8) host tensor, no H2D)
+        from .. import _native as N
+
+        ft = torch.as_tensor(focal, dtype=torch.float32).flatten()
+        fx, fy = (float(ft[0]), float(ft[0])) if ft.numel() == 1 else (float(ft[0]), float(ft[1]))
+        if c is None:
+            cx, cy = width * 0.5, height * 0.5
+        else:
+            cc = torch.as_tensor(c, dtype=torch.float32).flatten()
+            cx, cy = float(cc[0]), float(cc[-1])
+        p = poses.detach().float().contiguous()
+        rays = torch.empty(n, height, width, 8, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            N.check(N.lib().pnr_gen_rays(N.ptr(p), n, width, height, fx, fy, cx, cy, float(z_near), float(z_far),
+                                         N.ptr(rays), N.stream_ptr(dev)), "pnr_gen_rays")
+        return rays
     cam = unproj_map(width, height, torch.as_tensor(focal).squeeze(), c=c, device=dev)
     dirs = torch.matmul(poses[:, None, None, :3, :3], cam[None, ..., None])[..., 0]
     cen = poses[:, None, None, :3, 3].expand(-1, height, width, -1)
@@ -76,3 +92,24 @@ def pose_spherical(theta, phi, radius):
 def psnr(pred, target):
     mse = ((pred - target) ** 2).mean()
     return -10 * math.log10(mse)
+
+
+def finalize_frames(rgb, target=None):
+    """Device-side tail of the eval drivers: clamp to [0,1], quantise to uint8 (what gen_video writes)
+    and, with a ground-truth image, PSNR of the clamped frame -- all without a host sync.
+    :return (uint8 tensor like rgb, psnr 0-dim fp64 device tensor | None)"""
+    from .. import _native as N
+
+    if not rgb.is_cuda:
+        raise RuntimeError("pixelnerf_b200: finalize_frames needs CUDA tensors")
+    x = rgb.detach().float().contiguous()
+    u8 = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    gt = sse = None
+    if target is not None:
+        gt = target.detach().float().contiguous().to(x.device)
+        assert gt.shape == x.shape
+        sse = torch.zeros((), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        N.check(N.lib().pnr_finalize_rgb(N.ptr(x), N.ptr(gt), x.numel(), N.ptr(u8), N.ptr(sse), N.stream_ptr(x.device)),
+                "pnr_finalize_rgb")
+    return u8, (None if sse is None else -10.0 * torch.log10(sse / x.numel()))

@@ -148,3 +148,35 @@ def test_errors_are_loud():
         net(torch.zeros(1, 4, 3), coarse=True, viewdirs=torch.zeros(1, 4, 3))  # CPU tensors: no fallback
     with pytest.raises(AssertionError):
         net.mlp_coarse(torch.zeros(8, 17, device="cuda"))  # wrong row width (resnetfc.py:190)
+
+
+def test_gen_rays_on_device():
+    """device-side ray generation vs the oracle's gen_rays (itself bit-equal to the
+    reference's util.gen_rays on CPU)."""
+    import pixel_nerf_multiscale_b200 as pk
+
+    poses = torch.stack([po.pose_spherical(33.0, -12.0, 2.1), po.pose_spherical(-63.0, -10.0, 1.3),
+                         po.pose_spherical(170.0, 25.0, 3.0)])
+    for focal, c, W, H in ((torch.tensor([[72.3, 70.0]]), torch.tensor([[20.0, 15.0]]), 40, 30), (torch.tensor(119.4), None, 64, 64)):
+        ref = po.gen_rays(poses, W, H, focal, 0.1, 5.0, c)
+        got = pk.util.gen_rays(poses.cuda(), W, H, focal, 0.1, 5.0, c)
+        assert got.shape == ref.shape and got.is_cuda
+        assert maxabs(got.cpu(), ref) < 1e-6
+        assert torch.equal(got[..., :3].cpu(), ref[..., :3]) and torch.equal(got[..., 6:].cpu(), ref[..., 6:])
+
+
+def test_finalize_frames_on_device():
+    """clamp / uint8 / PSNR on the device vs the numpy/torch formulation of the drivers."""
+    import numpy as np
+    import pixel_nerf_multiscale_b200 as pk
+
+    g = torch.Generator().manual_seed(9)
+    rgb = torch.rand(3, 37, 41, 3, generator=g) * 1.4 - 0.2
+    gt = torch.rand(3, 37, 41, 3, generator=g)
+    u8, psnr = pk.util.finalize_frames(rgb.cuda(), gt.cuda())
+    ref_u8 = (rgb.clamp(0, 1).numpy() * 255).astype(np.uint8)
+    assert np.array_equal(u8.cpu().numpy(), ref_u8)
+    ref_psnr = pk.util.psnr(rgb.clamp(0, 1).double(), gt.double())
+    assert abs(psnr.item() - ref_psnr) < 1e-6
+    u8b, none = pk.util.finalize_frames(rgb.cuda())
+    assert none is None and torch.equal(u8b, u8)
