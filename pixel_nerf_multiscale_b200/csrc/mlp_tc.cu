@@ -1,20 +1,26 @@
-// Kernel (b), production path: ResnetFC (src/model/resnetfc.py:173-236) as a fused chain of
-// tcgen05 (UTCHMMA.2CTA) GEMMs with bf16 operands and fp32 accumulation in tensor memory.
+// Kernels (a)+(b), production path: fused point-feature gather + ResnetFC
+// (src/model/models.py.backup2:155-282, src/model/resnetfc.py:173-236) as a chain of tcgen05
+// (UTCHMMA.2CTA) GEMMs with bf16 operands and fp32 accumulation in tensor memory.
 //
 // Design ("pair-64"): a cluster of 2 CTAs owns a tile of 128 (point,view) rows, 64 rows per CTA, and
 // issues cta_group::2 MMAs with M=128, N=256, K=16.  Per CTA:
-//   TMEM  512 columns = X (64 rows x 512 fp32 residual stream, accumulated IN PLACE by lin_z and
+//   TMEM  512 columns = X (64 rows x 512 fp32 residual stream, accumulated IN PLACE by the lin_z and
 //         fc_1 GEMMs, so the residual add costs nothing and never leaves fp32) + NET (fc_0 output)
 //   smem  S_x = relu(x) bf16 (64 KB) and H = relu(net) bf16 (64 KB) as K-major SWIZZLE_NONE UMMA
-//         operands, a 5 x 16 KB ring of weight chunks and a 2 x 8 KB ring of [latent|code] slices,
-//         all filled by 1-D bulk copies (UBLKCP) from pre-packed global images.
-//   warps 0 producer | 1 MMA issuer (leader CTA) / barrier relay (peer CTA) | 2 TMEM alloc |
-//         4-11 epilogue (TMEM -> +bias, relu -> bf16 operand panels; view mean-pool; lin_out head)
-// Phase A (rows = points x views): lin_in+lin_z[0], blocks 0..combine_layer-1, view mean-pool
+//         operands + one ring of 6 x 16 KB slots carrying weight chunks and [latent|code] operand
+//         slices, filled by 2-D tiled TMA (UTMALDG.2D.2CTA) whose bytes complete on the leader CTA's
+//         mbarrier.  Weights are pre-packed into the exact shared-memory image, so a box of
+//         rows-of-256-bytes is a plain linear copy.
+//   warps 0 TMA producer | 1 MMA issuer (leader CTA only) | 2-3 gather (operand image of the NEXT tile;
+//         warp 2 also owns the TMEM allocation) | 4-11 epilogue (TMEM -> +bias, relu -> bf16 operand
+//         panels; view mean-pool; lin_out head).  Producer and issuer run warp-uniform, electing one
+//         lane only around the instruction, so descriptors live in uniform registers.
+// Phase A (rows = points x views): gather, lin_in+lin_z[0], blocks 0..combine_layer-1 with the next
+//         block's lin_z GEMM scheduled between fc_0 and fc_1, view mean-pool
 //         (util.combine_interleaved) -> pooled x (fp32) to global.
 // Phase B (rows = points): remaining blocks, lin_out, sigmoid/relu head (models.py.backup2:274-281).
-// The [latent|code] operand rows are produced by the bf16 variant of kernel (a) below
-// (128-bit gathers of the NHWC bf16 pyramid, written directly in UMMA panel order).
+// Every mbarrier wait is wall-clock bounded; a protocol fault writes its tag to pinned host memory
+// and traps (pnr_tc_check reports it) instead of hanging the GPU.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -53,8 +59,6 @@ constexpr int NB_ST = 6;                // unified operand ring: weight chunks (
 constexpr int NB_ST_B = 5;              // phase B: 5 slots, the 6th holds the lin_out weights / partial sums
 constexpr int B_SPLIT = 8;              // TMA boxes per weight chunk (2 KB each: small boxes land sooner)
 constexpr int A_SPLIT = 4;              // TMA boxes per operand slice
-constexpr int W_REPLICAS = 1;           // copies of the packed weights; pair p streams copy p % W_REPLICAS so that
-                                        // 74 pairs do not all hit the same L2 lines at the same time (measured: no effect -> 1)
 constexpr int OFF_SX = 0;
 constexpr int OFF_H = OFF_SX + ROWS * DH * 2;
 constexpr int OFF_BRING = OFF_H + ROWS * DH * 2;
@@ -80,7 +84,6 @@ struct Params {
   int ns, ppw;                         // views per point, points per CTA (= 64 / ns; rows pl*ns + v)
   long long P;                         // points
   int tilesA, tilesB;
-  uint32_t replica_stride;             // bytes between weight replicas
   const uint8_t* zc;                   // [tileA][cta][slice][A_SLICE]
   float* x3;                           // pooled residual stream, phase-B tile order
   float* out;                          // (P,4)
@@ -198,14 +201,13 @@ static Layout make_layout(const pnr_mlp& m) {
 
 size_t mlp_tc_packed_bytes(const pnr_mlp& m) {
   if (tc_supported(m) != PNR_OK) return 256;
-  return make_layout(m).total * W_REPLICAS;
+  return make_layout(m).total;
 }
 
 int mlp_tc_pack(const pnr_mlp& m, void* dst, size_t dst_bytes, cudaStream_t st) {
   PNR_TRY(tc_supported(m));
   Layout L = make_layout(m);
-  PNR_CHECK_ARG(dst_bytes >= L.total * W_REPLICAS, "mlp_pack: destination too small (%zu < %zu)", dst_bytes,
-                L.total * W_REPLICAS);
+  PNR_CHECK_ARG(dst_bytes >= L.total, "mlp_pack: destination too small (%zu < %zu)", dst_bytes, L.total);
   PNR_CHECK_ARG(((uintptr_t)dst & 15) == 0, "mlp_pack: destination must be 16-byte aligned");
   uint8_t* d = (uint8_t*)dst;
   auto pack = [&](const float* w, int K, int slices, uint32_t off) -> int {
@@ -243,8 +245,6 @@ int mlp_tc_pack(const pnr_mlp& m, void* dst, size_t dst_bytes, cudaStream_t st) 
   for (int b = 0; b < m.n_blocks; ++b) PNR_TRY(bias(m.fc0_b[b], nullptr, nullptr, nullptr, bias0 + (size_t)b * DH));
   PNR_CUDA(cudaMemcpyAsync(d + L.off_lin_out, m.lin_out_w, (size_t)4 * DH * 4, cudaMemcpyDeviceToDevice, st));
   PNR_CUDA(cudaMemcpyAsync(d + L.off_lin_out + (size_t)4 * DH * 4, m.lin_out_b, 16, cudaMemcpyDeviceToDevice, st));
-  for (int r = 1; r < W_REPLICAS; ++r)
-    PNR_CUDA(cudaMemcpyAsync(d + (size_t)r * L.total, d, L.total, cudaMemcpyDeviceToDevice, st));
   return PNR_OK;
 }
 
@@ -595,7 +595,7 @@ __device__ __forceinline__ void load_a(Ctx& cx, Ring& ra, const CUtensorMap* tm,
 }
 // weight chunk (slice s, column block nb) of a GEMM group for this CTA
 __device__ __forceinline__ uint32_t wchunk(uint32_t off, int s, int nb, uint32_t rank) {
-  return off + (uint32_t)((s * 2 + nb) * 2 + rank) * B_CHUNK;  // + replica base, added by the caller's `wb`
+  return off + (uint32_t)((s * 2 + nb) * 2 + rank) * B_CHUNK;
 }
 
 // ---- MMA side helpers -----------------------------------------------------------------------------
@@ -767,7 +767,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
     {
       Ring rb;
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST);
-      const uint32_t wb = (uint32_t)(pair % W_REPLICAS) * p.replica_stride;
       uint32_t git = 0;
       for (int tile = pair; tile < p.tilesA; tile += npairs, ++git) {
         if (p.fused_gather) {  // this CTA's rows of the tile have been gathered (and are visible to TMA)
@@ -778,19 +777,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
         const size_t zt = ((size_t)(tile * 2 + cx.rank) * nsl) * A_SLICE;
         for (int s = 0; s < nsl; ++s) {
           load_a(cx, rb, &p.tm_zc, zt + (size_t)s * A_SLICE);
-          for (int nb = 0; nb < 2; ++nb) load_b(cx, rb, &p.tm_w, wb + wchunk(p.off_g1[0], s, nb, cx.rank));
+          for (int nb = 0; nb < 2; ++nb) load_b(cx, rb, &p.tm_w, wchunk(p.off_g1[0], s, nb, cx.rank));
         }
         for (int b = 0; b < p.n_pre; ++b) {
           for (int nb = 0; nb < 2; ++nb)
-            for (int s = 0; s < DH / KS; ++s) load_b(cx, rb, &p.tm_w, wb + wchunk(p.off_g2[b], s, nb, cx.rank));
+            for (int s = 0; s < DH / KS; ++s) load_b(cx, rb, &p.tm_w, wchunk(p.off_g2[b], s, nb, cx.rank));
           if (b + 1 < p.n_pre)
             for (int s = 0; s < p.nks_z; ++s) {
               load_a(cx, rb, &p.tm_zc, zt + (size_t)s * A_SLICE);
-              for (int nb = 0; nb < 2; ++nb) load_b(cx, rb, &p.tm_w, wb + wchunk(p.off_g1[b + 1], s, nb, cx.rank));
+              for (int nb = 0; nb < 2; ++nb) load_b(cx, rb, &p.tm_w, wchunk(p.off_g1[b + 1], s, nb, cx.rank));
             }
           for (int sh = 0; sh < 2; ++sh)  // same quartered order as gemm_fc1
             for (int nb = 0; nb < 2; ++nb)
-              for (int s = sh * 4; s < sh * 4 + 4; ++s) load_b(cx, rb, &p.tm_w, wb + wchunk(p.off_g3[b], s, nb, cx.rank));
+              for (int s = sh * 4; s < sh * 4 + 4; ++s) load_b(cx, rb, &p.tm_w, wchunk(p.off_g3[b], s, nb, cx.rank));
         }
       }
       if (p.stats && cx.rank == 0 && lane == 0) {
@@ -881,7 +880,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
         nph ^= 1;
       }
       // ---- view mean-pool of the residual stream -> pooled x (fp32) in phase-B tile order ----
-      const long long tp0 = clock64();
       int v;
       bool valid;
       long long gp = tileA_point(tile, (int)cx.rank, e.row, p.ns, p.ppw, v, valid);
@@ -960,7 +958,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(cx.bar(XP_DONE), 0);
-      (void)tp0;
     }
     if (p.stats && cx.rank == 0 && warp == 4 && lane == 0) {
       unsigned long long* st = p.stats + (size_t)pair * 16;
@@ -1011,15 +1008,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
     {
       Ring rb;
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST_B);
-      const uint32_t wb = (uint32_t)(pair % W_REPLICAS) * p.replica_stride;
       for (int tile = pair; tile < p.tilesB; tile += npairs)
         for (int j = 0; j < p.n_post; ++j) {
           const int b = p.n_pre + j;
           for (int nb = 0; nb < 2; ++nb)
-            for (int s = 0; s < DH / KS; ++s) load_b(cx, rb, &p.tm_w, wb + wchunk(p.off_g2[b], s, nb, cx.rank));
+            for (int s = 0; s < DH / KS; ++s) load_b(cx, rb, &p.tm_w, wchunk(p.off_g2[b], s, nb, cx.rank));
           for (int sh = 0; sh < 2; ++sh)  // same quartered order as gemm_fc1
             for (int nb = 0; nb < 2; ++nb)
-              for (int s = sh * 4; s < sh * 4 + 4; ++s) load_b(cx, rb, &p.tm_w, wb + wchunk(p.off_g3[b], s, nb, cx.rank));
+              for (int s = sh * 4; s < sh * 4 + 4; ++s) load_b(cx, rb, &p.tm_w, wchunk(p.off_g3[b], s, nb, cx.rank));
         }
     }
   } else if (warp == 1) {
@@ -1150,7 +1146,6 @@ struct Plan {
   int ppw, ptile, tilesA, tilesB, nsl;
   uint8_t* zc;
   float* x3;
-  int* err;
   size_t total;
 };
 
@@ -1164,7 +1159,6 @@ static Plan make_plan(const Layout& L, int ns, long long P, void* ws, size_t ws_
   Arena a(ws, ws_bytes);
   pl.zc = a.take<uint8_t>((size_t)pl.tilesA * 2 * pl.nsl * A_SLICE);
   pl.x3 = a.take<float>((size_t)pl.tilesB * 128 * DH);
-  pl.err = a.take<int>(4);
   pl.total = a.off + 256;
   return pl;
 }
@@ -1276,8 +1270,7 @@ static int run_phases(const pnr_mlp& m, const Layout& L, const Plan& pl, int ns,
   PNR_TRY(ensure_err_word());
   p.err = g_err_dev;
   p.stats = g_stats_ptr;
-  p.replica_stride = (uint32_t)L.total;
-  PNR_TRY(encode_rows256(&p.tm_w, m.packed, L.total * W_REPLICAS, B_CHUNK / B_SPLIT / 256));
+  PNR_TRY(encode_rows256(&p.tm_w, m.packed, L.total, B_CHUNK / B_SPLIT / 256));
   PNR_TRY(encode_rows256(&p.tm_zc, pl.zc, (size_t)pl.tilesA * 2 * pl.nsl * A_SLICE, A_SLICE / A_SPLIT / 256));
   {
     ProfScope ps(PROF_PHASE_A, 2.0 * mac_pre * (double)P * ns, 0.0, st);
@@ -1320,14 +1313,13 @@ int net_forward_tc(const pnr_scene& sc, const pnr_mlp& m, const float* xyz, cons
   PNR_UNSUPPORTED(sc.feat_dtype != PNR_BF16, "bf16 path needs a bf16-packed pyramid");
   for (int l = 0; l < sc.n_levels; ++l)
     PNR_UNSUPPORTED(sc.C[l] % 8 != 0 || sc.ch_off[l] % 8 != 0, "bf16 gather needs channel counts that are multiples of 8");
-  PNR_CHECK_ARG(m.packed_bytes >= make_layout(m).total * W_REPLICAS, "mlp.packed image too small");
+  PNR_CHECK_ARG(m.packed_bytes >= make_layout(m).total, "mlp.packed image too small");
   Layout L = make_layout(m);
   Plan pl = make_plan(L, sc.ns, P, ws, ws_bytes);
   if (pl.total > ws_bytes + 256 || !ws) {
     set_err("net_forward_tc: workspace too small (%zu < %zu)", ws_bytes, pl.total);
     return PNR_ERR_WORKSPACE;
   }
-  PNR_CUDA(cudaMemsetAsync(pl.err, 0, 16, st));
   static const bool fused = [] {
     const char* e = getenv("PNR_FUSED_GATHER");
     return !(e && e[0] == '0');
@@ -1358,14 +1350,13 @@ int mlp_forward_tc_rows(const pnr_mlp& m, const float* zx, int SB, int NS, int P
   PNR_TRY(tc_supported(m));
   PNR_UNSUPPORTED(NS > 32, "more than 32 source views per object");
   Layout L = make_layout(m);
-  PNR_CHECK_ARG(m.packed_bytes >= L.total * W_REPLICAS, "mlp.packed image too small");
+  PNR_CHECK_ARG(m.packed_bytes >= L.total, "mlp.packed image too small");
   long long pts = (long long)SB * P;
   Plan pl = make_plan(L, NS, pts, ws, ws_bytes);
   if (pl.total > ws_bytes + 256 || !ws) {
     set_err("mlp_forward_tc: workspace too small (%zu < %zu)", ws_bytes, pl.total);
     return PNR_ERR_WORKSPACE;
   }
-  PNR_CUDA(cudaMemsetAsync(pl.err, 0, 16, st));
   long long wrows = (long long)pl.tilesA * 128;
   rows_to_operand_kernel<<<(unsigned)ceil_div_ll(wrows, 8), 256, 0, st>>>(zx, m.d_latent, m.d_in, SB, NS, P, pl.ppw,
                                                                         pl.tilesA, L.nks_z, L.nks_c, pl.zc);

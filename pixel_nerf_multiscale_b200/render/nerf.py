@@ -89,10 +89,7 @@ class NeRFRenderer(torch.nn.Module):
         if tape is not None:
             return tape
 
-        class _Lazy(dict):
-            pass
-
-        t = _Lazy()
+        t = {}
         t["coarse"] = torch.rand(B, kc, dtype=torch.float32, device=device)
         if self.using_fine:
             if kf - kd > 0:

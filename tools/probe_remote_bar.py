@@ -1,3 +1,5 @@
+"""Probe (negative result kept on purpose): a non-tensor cp.async.bulk cannot complete on the LEADER CTA's
+mbarrier of a cta_group::2 pair -- the leader times out (tag 102); the tensor (TMA) form with .cta_group::2 can."""
 import sys, os; sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(),'tests'))
 import torch
 from test_gpu_tc_probe import _probe

@@ -1,3 +1,5 @@
+"""Per-role cycle counters of the phase-A kernel.  Needs a library built with
+PNR_EXTRA_NVCC_FLAGS=-DPNR_TC_STATS=1 pixel_nerf_multiscale_b200/csrc/build.sh"""
 import sys, os, ctypes as C
 sys.path.insert(0, os.getcwd())
 import torch, bench
