@@ -316,8 +316,8 @@ def main():
             traffic = None
             try:  # DRAM bytes of one launch of this kernel from the committed ncu --set full capture
                 prof = json.load(open(os.path.join(REPO, "profiles", "r01_v5_ncu_summary.json")))["mlp_phaseA_kernel"]
-                unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-                traffic = sum(float(prof[k][0]) * unit[prof[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+                traffic = sum(float(prof[k][0]) * scale[prof[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
             except Exception:
                 pass
             roof = {"bound": "tensor", "kernel": "mlp_phaseA_kernel (fused gather + ResnetFC blocks 0..combine_layer-1 + view pool, tcgen05 cta_group::2)",
