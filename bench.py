@@ -192,7 +192,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    wl_name = args.workload or ("c2" if args.gpus == 1 else "c3")
+    # same workload at every N so that the per-N values form one (weak) scaling series
+    wl_name = args.workload or "c2"
     wl = WORKLOADS[wl_name]
     metric, unit = "rays/sec", "rays/s"
     config = {"workload": "%s: %s; %d rays/step, 64 coarse + 32 fine (16 depth) samples, 2 MLPs" % (wl_name, wl["desc"], wl["rays"]),
