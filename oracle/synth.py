@@ -27,6 +27,9 @@ CASES = {
     "dtu_ns3": dict(ns=3, sb=1, H=30, W=40, focal=(72.3, 72.3), c=(20.0, 15.0), levels=[(256, 19, 25)],
                     z_near=0.1, z_far=5.0, radius=2.2, conf="conf/exp/dtu.conf", multi_scale=False, rays=96,
                     white_bkgd=False),
+    # the single-view base schema: 3 blocks, never pooled (combine_layer defaults to 1000), lin_z in every block
+    "sv3_ns1": dict(ns=1, sb=1, H=32, W=32, focal=40.0, c=None, levels=[(256, 9, 11)], z_near=1.2, z_far=4.0,
+                    radius=2.6, conf="conf/default.conf", multi_scale=False, rays=64, white_bkgd=True),
     "ms_ns3_sb2": dict(ns=3, sb=2, H=30, W=40, focal=(72.3, 72.3), c=(20.0, 15.0),
                        levels=[(64, 15, 20), (64, 15, 20), (128, 8, 10), (256, 4, 5)], z_near=0.5, z_far=4.5,
                        radius=2.2, conf="conf/exp/dtu.conf", multi_scale=True, rays=64, white_bkgd=False),

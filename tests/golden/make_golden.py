@@ -115,9 +115,12 @@ VARIANTS = {
     "ms_ns2": {"default": {}},
     "dtu_ns3": {"default": {}},
     "ms_ns3_sb2": {"default": {}},
+    "sv3_ns1": {"default": {}},
 }
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    only = sys.argv[1:]
     for name, var in VARIANTS.items():
-        run_case(name, var)
+        if not only or name in only:
+            run_case(name, var)

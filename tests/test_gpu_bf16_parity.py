@@ -14,7 +14,7 @@ from helpers import (N_POINTS, RENDER_SEED, build_product, load_golden, make_ren
                      sample_points)
 
 pytestmark = pytest.mark.gpu
-CASES = ["ss_ns1", "ms_ns2", "dtu_ns3", "ms_ns3_sb2"]
+CASES = ["ss_ns1", "ms_ns2", "dtu_ns3", "ms_ns3_sb2", "sv3_ns1"]
 
 
 def _tc_check():
@@ -41,7 +41,7 @@ def _bf16_ref_mlp(sd, zx, d_latent, n_blocks, combine_layer, dims):
     return lin(torch.relu(x), "lin_out")
 
 
-@pytest.mark.parametrize("ns,p", [(1, 64), (2, 37), (3, 200), (1, 300), (3, 41)])
+@pytest.mark.parametrize("ns,p", [(1, 64), (2, 37), (3, 200), (1, 300), (3, 41), (4, 50), (5, 77), (7, 33)])
 def test_mlp_rows_bf16(ns, p):
     from pixel_nerf_multiscale_b200 import _native as N
 

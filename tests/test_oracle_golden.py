@@ -12,7 +12,7 @@ from oracle import pixelnerf_oracle as po
 from oracle import synth
 from helpers import (N_POINTS, RENDER_SEED, load_conf, load_golden, maxabs, renderer_kwargs, sample_points)
 
-CASES = ["ss_ns1", "ms_ns2", "dtu_ns3", "ms_ns3_sb2"]
+CASES = ["ss_ns1", "ms_ns2", "dtu_ns3", "ms_ns3_sb2", "sv3_ns1"]
 
 
 @pytest.mark.parametrize("name", CASES)
