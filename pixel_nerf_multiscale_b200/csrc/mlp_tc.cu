@@ -692,8 +692,23 @@ __device__ __forceinline__ Epi make_epi(int warp, int lane) {
 // feature index of column i of the 32-column group (nb, half) held by this thread
 __device__ __forceinline__ int feat0(const Epi& e, int nb, int half) { return nb * 256 + e.h * 128 + e.cs * 64 + half * 32; }
 
+// Biases of the 64 features (2 halves x 32 columns) one epilogue thread handles in column block nb.
+// With ~225 KB of the SM given to shared memory there is almost no L1 left, so a bias load is an L2
+// round trip (~700 cycles): the loads are issued BEFORE the mbarrier wait that precedes the stage.
+struct BiasRegs {
+  float4 v[16];
+};
+__device__ __forceinline__ void prefetch_bias(BiasRegs& b, const Epi& e, const float* __restrict__ bias, int nb) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const float4* b4 = reinterpret_cast<const float4*>(bias + feat0(e, nb, half));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b.v[half * 8 + j] = __ldg(b4 + j);
+  }
+}
+
 // TMEM (64 columns of block nb) -> relu(v + bias) -> bf16 operand panels in `dst_off`; publishes slice
-__device__ __forceinline__ void epi_to_operand(const Ctx& cx, const Epi& e, uint32_t col, int nb, const float* __restrict__ bias,
+__device__ __forceinline__ void epi_to_operand(const Ctx& cx, const Epi& e, uint32_t col, int nb, const BiasRegs& bias,
                                                uint32_t dst_off, int ready_bar0) {
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
@@ -701,10 +716,9 @@ __device__ __forceinline__ void epi_to_operand(const Ctx& cx, const Epi& e, uint
     tmem_ld32(cx.tmem + e.lane_addr + col + nb * 128 + e.cs * 64 + half * 32, r);
     tmem_ld_wait();
     const int f0 = feat0(e, nb, half);
-    const float4* b4 = reinterpret_cast<const float4*>(bias + f0);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {  // 8 features -> one 16-byte k-group entry
-      float4 ba = __ldg(b4 + 2 * j), bb = __ldg(b4 + 2 * j + 1);
+      const float4 ba = bias.v[half * 8 + 2 * j], bb = bias.v[half * 8 + 2 * j + 1];
       float v0 = fmaxf(__uint_as_float(r[8 * j + 0]) + ba.x, 0.f), v1 = fmaxf(__uint_as_float(r[8 * j + 1]) + ba.y, 0.f);
       float v2 = fmaxf(__uint_as_float(r[8 * j + 2]) + ba.z, 0.f), v3 = fmaxf(__uint_as_float(r[8 * j + 3]) + ba.w, 0.f);
       float v4 = fmaxf(__uint_as_float(r[8 * j + 4]) + bb.x, 0.f), v5 = fmaxf(__uint_as_float(r[8 * j + 5]) + bb.y, 0.f);
@@ -862,19 +876,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
       const uint32_t xcol = (it & 1) ? 256u : 0u, netcol = 256u - xcol;
       for (int b = 0; b < p.n_pre; ++b) {
         long long t0 = 0;
+        BiasRegs br;
         for (int nb = 0; nb < 2; ++nb) {
+          prefetch_bias(br, e, biasA + (size_t)b * DH, nb);
           twait(cx, 0, cx.bar(X_READY + nb), xph, 401 + nb * 1000 + (int)it * 10000 + warp * 1000000 + (int)cx.rank * 100000000);
           tc_fence_after();
           t0 = clock64();
-          epi_to_operand(cx, e, xcol, nb, biasA + (size_t)b * DH, OFF_SX, SX_READY);
+          epi_to_operand(cx, e, xcol, nb, br, OFF_SX, SX_READY);
           cx.w[2] += clock64() - t0;
         }
         xph ^= 1;
         for (int nb = 0; nb < 2; ++nb) {
+          prefetch_bias(br, e, bias0 + (size_t)b * DH, nb);
           twait(cx, 1, cx.bar(NET_READY + nb), nph, 402 + nb);
           tc_fence_after();
           t0 = clock64();
-          epi_to_operand(cx, e, netcol, nb, bias0 + (size_t)b * DH, OFF_H, H_READY);
+          epi_to_operand(cx, e, netcol, nb, br, OFF_H, H_READY);
           cx.w[3] += clock64() - t0;
         }
         nph ^= 1;
@@ -899,6 +916,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
       const int pair_id = e.h * 2 + e.cs;                 // warps (q even, q odd) with equal h, cs
       float4* spill = reinterpret_cast<float4*>(smem_raw + OFF_SX) + (size_t)pair_id * (2 * 2 * 8);
       for (int nb = 0; nb < 2; ++nb) {
+        BiasRegs bp;
+        prefetch_bias(bp, e, bP, nb);
         twait(cx, 0, cx.bar(X_READY + nb), xph, 405 + nb * 1000 + (int)it * 10000 + warp * 1000000);
         tc_fence_after();
         const long long tq0 = clock64();
@@ -929,7 +948,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
           // x3[tileB][ctaB][nb][h][jq (32)][row (64)][4]
           float4* dst = reinterpret_cast<float4*>(p.x3) +
                         ((((tb * 2 + cb) * 2 + nb) * 2 + e.h) * 32 + (e.cs * 16 + half * 8)) * 64 + rb_;
-          const float4* b4 = reinterpret_cast<const float4*>(bP + f0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float s4[4];
@@ -947,7 +965,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
               s4[0] += u.x; s4[1] += u.y; s4[2] += u.z; s4[3] += u.w;
             }
             if (valid) {
-              const float4 bb = __ldg(b4 + j);
+              const float4 bb = bp.v[half * 8 + j];
               dst[(size_t)j * 64] = make_float4(s4[0] * inv + bb.x, s4[1] * inv + bb.y, s4[2] * inv + bb.z, s4[3] * inv + bb.w);
             }
           }
@@ -1072,17 +1090,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
       }
       for (int j = 0; j < p.n_post; ++j) {
         const int b = p.n_pre + j;
+        BiasRegs br;
         for (int nb = 0; nb < 2; ++nb) {
+          prefetch_bias(br, e, bias0 + (size_t)b * DH, nb);
           mbar_wait(cx.bar(NET_READY + nb), nph, cx.err, 502 + nb);
           tc_fence_after();
-          epi_to_operand(cx, e, netcol, nb, bias0 + (size_t)b * DH, OFF_H, H_READY);
+          epi_to_operand(cx, e, netcol, nb, br, OFF_H, H_READY);
         }
         nph ^= 1;
         if (j + 1 < p.n_post) {
           for (int nb = 0; nb < 2; ++nb) {
+            prefetch_bias(br, e, biasB + (size_t)(j + 1) * DH, nb);
             mbar_wait(cx.bar(X_READY + nb), xph, cx.err, 501);
             tc_fence_after();
-            epi_to_operand(cx, e, xcol, nb, biasB + (size_t)(j + 1) * DH, OFF_SX, SX_READY);
+            epi_to_operand(cx, e, xcol, nb, br, OFF_SX, SX_READY);
           }
           xph ^= 1;
         }
@@ -1091,6 +1112,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
       const float* bO = biasB + (size_t)p.n_post * DH;
       float part[4] = {0.f, 0.f, 0.f, 0.f};
       for (int nb = 0; nb < 2; ++nb) {
+        BiasRegs bo;
+        prefetch_bias(bo, e, bO, nb);
         if (p.n_post > 0) {
           mbar_wait(cx.bar(X_READY + nb), xph, cx.err, 505);
           tc_fence_after();
@@ -1102,10 +1125,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
           tmem_ld_wait();
           const int f0 = feat0(e, nb, half);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float x = fmaxf(__uint_as_float(r[i]) + __ldg(bO + f0 + i), 0.f);
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = bo.v[half * 8 + j];
+            const float xs[4] = {fmaxf(__uint_as_float(r[4 * j + 0]) + bb.x, 0.f), fmaxf(__uint_as_float(r[4 * j + 1]) + bb.y, 0.f),
+                                 fmaxf(__uint_as_float(r[4 * j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(r[4 * j + 3]) + bb.w, 0.f)};
 #pragma unroll
-            for (int o = 0; o < 4; ++o) part[o] = fmaf(x, s_wout[o * DH + f0 + i], part[o]);
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int o = 0; o < 4; ++o) part[o] = fmaf(xs[i], s_wout[o * DH + f0 + 4 * j + i], part[o]);
           }
         }
       }
