@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpixelnerf_b200.so")
+# PIXELNERF_B200_LIB: alternative build of the same library (A/B timing of kernel variants on one box).
+LIB_PATH = os.environ.get("PIXELNERF_B200_LIB") or os.path.join(_HERE, "libpixelnerf_b200.so")
 
 FP32, BF16 = 0, 1
 MAX_LEVELS, MAX_BLOCKS = 8, 8

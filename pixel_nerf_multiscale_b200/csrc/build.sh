@@ -2,15 +2,16 @@
 # Builds libpixelnerf_b200.so in-tree for sm_100a (the only supported target).
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
-OUT="$HERE/../libpixelnerf_b200.so"
+OUT="${PNR_OUT:-$HERE/../libpixelnerf_b200.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr ${PNR_EXTRA_NVCC_FLAGS}"
-mkdir -p "$HERE/build"
+BUILD="${PNR_BUILD_DIR:-$HERE/build}"
+mkdir -p "$BUILD"
 pids=()
 for f in api features mlp_f32 rays mlp_tc tc_probe; do
-  ( $NVCC $FLAGS -c "$HERE/$f.cu" -o "$HERE/build/$f.o" ) &
+  ( $NVCC $FLAGS -c "$HERE/$f.cu" -o "$BUILD/$f.o" ) &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$HERE"/build/{api,features,mlp_f32,rays,mlp_tc,tc_probe}.o -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$BUILD"/{api,features,mlp_f32,rays,mlp_tc,tc_probe}.o -lcudart
 echo "built $OUT"

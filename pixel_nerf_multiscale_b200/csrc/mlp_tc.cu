@@ -750,6 +750,111 @@ __device__ __forceinline__ void setup_barriers(const Ctx& cx) {
   fence_mbar_init();
 }
 
+// View mean-pool of one tile's residual stream (TMEM X) -> pooled x (fp32) in phase-B tile order.
+// Runs once per tile, i.e. with cold instruction cache lines every time (the kernel is far larger
+// than the I-cache and the other roles keep running): one compact out-of-line body per view count,
+// selected once, instead of code specialised on p.ns inline (which spread the executed path over
+// ~100 KB of SASS and cost ~10K cycles per tile in instruction fetch alone).  NS = 0: any view count.
+template <int NS>
+__device__ __noinline__ long long pool_tile(const Params& p, Ctx cx, const Epi e, int tile, uint32_t xcol, uint32_t xph,
+                                            uint32_t it, uint8_t* smem_raw) {
+  const int ns = NS ? NS : p.ns;
+  const int lane = e.lane;
+  const float* biasA = reinterpret_cast<const float*>(p.w + p.off_biasA);
+  int v;
+  bool valid;
+  long long gp = tileA_point(tile, (int)cx.rank, e.row, ns, p.ppw, v, valid);
+  valid = valid && v == 0 && gp < p.P;
+  const float* bP = biasA + (size_t)p.n_pre * DH;
+  const float inv = 1.0f / (float)ns;
+  const long long tb = gp >> 7;
+  const int cb = (int)((gp >> 6) & 1), rb_ = (int)(gp & 63);
+  // A point whose NS rows straddle lanes 31|32 (NS not a divisor of 32) has its first `rem` rows in
+  // the lower warp and the other NS-rem in the partner warp (same columns, next TMEM quadrant):
+  // the upper warp pre-sums its rows and hands one value per column over through the idle S_x.
+  const int rem = 32 % ns, nup = ns - rem;
+  const bool straddle = rem != 0;
+  const bool upper = (e.q & 1) != 0;
+  const bool takes_spill = straddle && !upper && lane == 32 - rem;
+  const int pair_id = e.h * 2 + e.cs;                 // warps (q even, q odd) with equal h, cs
+  float4* spill = reinterpret_cast<float4*>(smem_raw + OFF_SX) + (size_t)pair_id * (2 * 2 * 8);
+  long long work = 0;
+#pragma unroll 1
+  for (int nb = 0; nb < 2; ++nb) {
+    BiasRegs bp;
+    prefetch_bias(bp, e, bP, nb);
+    twait(cx, 0, cx.bar(X_READY + nb), xph, 405 + nb * 1000 + (int)it * 10000);
+    tc_fence_after();
+    const long long tq0 = clock64();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {  // (unrolled: bp.v is indexed by half)
+      uint32_t r[32];
+      tmem_ld32(cx.tmem + e.lane_addr + xcol + nb * 128 + e.cs * 64 + half * 32, r);
+      tmem_ld_wait();
+      float4* sp = spill + (nb * 2 + half) * 8;  // 32 columns
+      if (straddle) {
+        if (upper) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float u[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float x = __uint_as_float(r[4 * j + i]);
+              float a = __shfl_sync(0xffffffffu, x, 0);
+              if (NS) {
+#pragma unroll
+                for (int k = 1; k < (NS ? NS - 32 % (NS ? NS : 1) : 1); ++k) a += __shfl_sync(0xffffffffu, x, k);
+              } else {
+#pragma unroll 1
+                for (int k = 1; k < nup; ++k) a += __shfl_sync(0xffffffffu, x, k);
+              }
+              u[i] = a;
+            }
+            if (lane == 0) sp[j] = make_float4(u[0], u[1], u[2], u[3]);
+          }
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + pair_id) : "memory");
+      }
+      // x3[tileB][ctaB][nb][h][jq (32)][row (64)][4]
+      float4* dst = reinterpret_cast<float4*>(p.x3) +
+                    ((((tb * 2 + cb) * 2 + nb) * 2 + e.h) * 32 + (e.cs * 16 + half * 8)) * 64 + rb_;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float s4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float x = __uint_as_float(r[4 * j + i]);
+          float s = x;
+          if (NS) {
+#pragma unroll
+            for (int k = 1; k < NS; ++k) {
+              const float y = __shfl_down_sync(0xffffffffu, x, k);
+              s += (lane + k <= 31) ? y : 0.f;
+            }
+          } else {
+#pragma unroll 1
+            for (int k = 1; k < ns; ++k) {
+              const float y = __shfl_down_sync(0xffffffffu, x, k);
+              s += (lane + k <= 31) ? y : 0.f;
+            }
+          }
+          s4[i] = s;
+        }
+        if (takes_spill) {
+          const float4 u = sp[j];
+          s4[0] += u.x; s4[1] += u.y; s4[2] += u.z; s4[3] += u.w;
+        }
+        if (valid) {
+          const float4 bb = bp.v[half * 8 + j];
+          dst[(size_t)j * 64] = make_float4(s4[0] * inv + bb.x, s4[1] * inv + bb.y, s4[2] * inv + bb.z, s4[3] * inv + bb.w);
+        }
+      }
+    }
+    work += clock64() - tq0;
+  }
+  return work;
+}
+
 // =============================================================================================
 // Phase A
 // =============================================================================================
@@ -789,21 +894,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
           __syncwarp();
         }
         const size_t zt = ((size_t)(tile * 2 + cx.rank) * nsl) * A_SLICE;
+        // (loops deliberately not unrolled: instruction footprint, see mbar_wait_slow)
         for (int s = 0; s < nsl; ++s) {
           load_a(cx, rb, &p.tm_zc, zt + (size_t)s * A_SLICE);
           for (int nb = 0; nb < 2; ++nb) load_b(cx, rb, &p.tm_w, wchunk(p.off_g1[0], s, nb, cx.rank));
         }
         for (int b = 0; b < p.n_pre; ++b) {
-          for (int nb = 0; nb < 2; ++nb)
-            for (int s = 0; s < DH / KS; ++s) load_b(cx, rb, &p.tm_w, wchunk(p.off_g2[b], s, nb, cx.rank));
-          if (b + 1 < p.n_pre)
+          for (int c = 0; c < 2 * (DH / KS); ++c)  // nb-outer, s-inner
+            load_b(cx, rb, &p.tm_w, wchunk(p.off_g2[b], c % (DH / KS), c / (DH / KS), cx.rank));
+          if (b + 1 < p.n_pre) {
             for (int s = 0; s < p.nks_z; ++s) {
               load_a(cx, rb, &p.tm_zc, zt + (size_t)s * A_SLICE);
               for (int nb = 0; nb < 2; ++nb) load_b(cx, rb, &p.tm_w, wchunk(p.off_g1[b + 1], s, nb, cx.rank));
             }
-          for (int sh = 0; sh < 2; ++sh)  // same quartered order as gemm_fc1
-            for (int nb = 0; nb < 2; ++nb)
-              for (int s = sh * 4; s < sh * 4 + 4; ++s) load_b(cx, rb, &p.tm_w, wchunk(p.off_g3[b], s, nb, cx.rank));
+          }
+          for (int c = 0; c < 16; ++c)  // same quartered order as gemm_fc1: (sh, nb, s4) = (c/8, (c/4)%2, c%4)
+            load_b(cx, rb, &p.tm_w, wchunk(p.off_g3[b], (c >> 3) * 4 + (c & 3), (c >> 2) & 1, cx.rank));
         }
       }
       if (p.stats && cx.rank == 0 && lane == 0) {
@@ -897,81 +1003,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
         nph ^= 1;
       }
       // ---- view mean-pool of the residual stream -> pooled x (fp32) in phase-B tile order ----
-      int v;
-      bool valid;
-      long long gp = tileA_point(tile, (int)cx.rank, e.row, p.ns, p.ppw, v, valid);
-      valid = valid && v == 0 && gp < p.P;
-      const float* bP = biasA + (size_t)p.n_pre * DH;
-      const float inv = 1.0f / (float)p.ns;
-      const long long tb = gp >> 7;
-      const int cb = (int)((gp >> 6) & 1), rb_ = (int)(gp & 63);
-      // A point whose NS rows straddle lanes 31|32 (NS not a divisor of 32) has its first `rem` rows in
-      // the lower warp and the other NS-rem in the partner warp (same columns, next TMEM quadrant):
-      // the upper warp pre-sums its rows and hands one value per column over through the idle S_x.
-      const int rem = 32 % p.ns, nup = p.ns - rem;
-      const bool straddle = rem != 0;
-      const bool upper = (e.q & 1) != 0;
-      const bool in1 = lane + 1 <= 31, in2 = lane + 2 <= 31;
-      const bool takes_spill = straddle && !upper && lane == 32 - rem;
-      const int pair_id = e.h * 2 + e.cs;                 // warps (q even, q odd) with equal h, cs
-      float4* spill = reinterpret_cast<float4*>(smem_raw + OFF_SX) + (size_t)pair_id * (2 * 2 * 8);
-      for (int nb = 0; nb < 2; ++nb) {
-        BiasRegs bp;
-        prefetch_bias(bp, e, bP, nb);
-        twait(cx, 0, cx.bar(X_READY + nb), xph, 405 + nb * 1000 + (int)it * 10000 + warp * 1000000);
-        tc_fence_after();
-        const long long tq0 = clock64();
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t r[32];
-          tmem_ld32(cx.tmem + e.lane_addr + xcol + nb * 128 + e.cs * 64 + half * 32, r);
-          tmem_ld_wait();
-          float4* sp = spill + (nb * 2 + half) * 8;  // 32 columns
-          if (straddle) {
-            if (upper) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float u[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float x = __uint_as_float(r[4 * j + i]);
-                  float a = __shfl_sync(0xffffffffu, x, 0);
-                  for (int k = 1; k < nup; ++k) a += __shfl_sync(0xffffffffu, x, k);
-                  u[i] = a;
-                }
-                if (lane == 0) sp[j] = make_float4(u[0], u[1], u[2], u[3]);
-              }
-            }
-            asm volatile("bar.sync %0, 64;" ::"r"(2 + pair_id) : "memory");
-          }
-          const int f0 = feat0(e, nb, half);
-          // x3[tileB][ctaB][nb][h][jq (32)][row (64)][4]
-          float4* dst = reinterpret_cast<float4*>(p.x3) +
-                        ((((tb * 2 + cb) * 2 + nb) * 2 + e.h) * 32 + (e.cs * 16 + half * 8)) * 64 + rb_;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float s4[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float x = __uint_as_float(r[4 * j + i]);
-              float s = x;
-              if (p.ns > 1) { float y = __shfl_down_sync(0xffffffffu, x, 1); s += in1 ? y : 0.f; }
-              if (p.ns > 2) { float y = __shfl_down_sync(0xffffffffu, x, 2); s += in2 ? y : 0.f; }
-              for (int k = 3; k < p.ns; ++k) { float y = __shfl_down_sync(0xffffffffu, x, k); s += (lane + k <= 31) ? y : 0.f; }
-              s4[i] = s;
-            }
-            if (takes_spill) {
-              const float4 u = sp[j];
-              s4[0] += u.x; s4[1] += u.y; s4[2] += u.z; s4[3] += u.w;
-            }
-            if (valid) {
-              const float4 bb = bp.v[half * 8 + j];
-              dst[(size_t)j * 64] = make_float4(s4[0] * inv + bb.x, s4[1] * inv + bb.y, s4[2] * inv + bb.z, s4[3] * inv + bb.w);
-            }
-          }
-        }
-        cx.w[4] += clock64() - tq0;  // pool work only (waits excluded)
+      long long tp;
+      switch (p.ns) {
+        case 1: tp = pool_tile<1>(p, cx, e, tile, xcol, xph, it, smem_raw); break;
+        case 2: tp = pool_tile<2>(p, cx, e, tile, xcol, xph, it, smem_raw); break;
+        case 3: tp = pool_tile<3>(p, cx, e, tile, xcol, xph, it, smem_raw); break;
+        case 4: tp = pool_tile<4>(p, cx, e, tile, xcol, xph, it, smem_raw); break;
+        default: tp = pool_tile<0>(p, cx, e, tile, xcol, xph, it, smem_raw); break;
       }
+      cx.w[4] += tp;  // pool work only (waits excluded)
       xph ^= 1;
       tc_fence_before();
       __syncwarp();
@@ -981,6 +1021,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
       unsigned long long* st = p.stats + (size_t)pair * 16;
       st[9] = clock64() - t_begin;
       for (int i = 0; i < 5; ++i) st[10 + i] = cx.w[i];
+#if PNR_TC_STATS
+      p.stats[74 * 18 + pair] = it;  // tiles this pair processed
+#endif
     }
   }
   __syncwarp();
@@ -1029,11 +1072,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
       for (int tile = pair; tile < p.tilesB; tile += npairs)
         for (int j = 0; j < p.n_post; ++j) {
           const int b = p.n_pre + j;
-          for (int nb = 0; nb < 2; ++nb)
-            for (int s = 0; s < DH / KS; ++s) load_b(cx, rb, &p.tm_w, wchunk(p.off_g2[b], s, nb, cx.rank));
-          for (int sh = 0; sh < 2; ++sh)  // same quartered order as gemm_fc1
-            for (int nb = 0; nb < 2; ++nb)
-              for (int s = sh * 4; s < sh * 4 + 4; ++s) load_b(cx, rb, &p.tm_w, wchunk(p.off_g3[b], s, nb, cx.rank));
+#pragma unroll 1
+          for (int c = 0; c < 2 * (DH / KS); ++c)  // nb-outer, s-inner
+            load_b(cx, rb, &p.tm_w, wchunk(p.off_g2[b], c % (DH / KS), c / (DH / KS), cx.rank));
+#pragma unroll 1
+          for (int c = 0; c < 16; ++c)  // same quartered order as gemm_fc1: (sh, nb, s4) = (c/8, (c/4)%2, c%4)
+            load_b(cx, rb, &p.tm_w, wchunk(p.off_g3[b], (c >> 3) * 4 + (c & 3), (c >> 2) & 1, cx.rank));
         }
     }
   } else if (warp == 1) {

@@ -77,13 +77,10 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int tag) {
-  // try_wait itself suspends the thread for a hardware-bounded interval, so this loop does not
-  // spin hot.  (Default .acquire.cta semantics on purpose: a cluster-scope acquire makes ptxas emit
-  // CCTL.IVALL -- a full L1 invalidate -- after every probe, which dominated the first profile.)
-  // Wall-clock bound: 1 s without progress records `tag` in *err; once *err is set every wait in the
-  // grid gives up immediately, so a protocol bug drains the kernel in about a second.
-  if (mbar_try_wait(bar, parity)) return;
+// Slow path kept OUT OF LINE: the kernels wait at ~40 sites, and the instruction footprint of the
+// role loops matters (the L1.5 I-cache is 32 KB; code beyond it streams from an L2 that is busy with
+// the weight stream).
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* err, int tag) {
   unsigned long long t0 = 0;
   for (uint32_t it = 1;; ++it) {
     if (mbar_try_wait(bar, parity)) return;
@@ -102,6 +99,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
       }
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int tag) {
+  // try_wait itself suspends the thread for a hardware-bounded interval, so this loop does not
+  // spin hot.  (Default .acquire.cta semantics on purpose: a cluster-scope acquire makes ptxas emit
+  // CCTL.IVALL -- a full L1 invalidate -- after every probe, which dominated the first profile.)
+  // Wall-clock bound: 1 s without progress records `tag` in *err; once *err is set every wait in the
+  // grid gives up immediately, so a protocol bug drains the kernel in about a second.
+  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity, err, tag);
 }
 
 // ---- async proxy / bulk copy ---------------------------------------------------------------------
