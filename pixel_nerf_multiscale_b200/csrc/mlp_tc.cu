@@ -1063,7 +1063,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
   tc_fence_after();
   cx.tmem = *tmem_slot;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const uint32_t xcol = 0, netcol = 256;
+  // X and NET swap TMEM halves from tile to tile: the next tile's pooled x is loaded into the NET
+  // half (and S_x) while the last fc_1 of the current tile still runs, so only the read of the final
+  // X (not the x3 load) separates two tiles on the tensor pipe.
 
   if (warp == 0) {
     {
@@ -1084,37 +1086,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
     if (cx.rank == 0) {
       Ring rb;
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST_B);
-      uint32_t use = 0;
-      for (int tile = pair; tile < p.tilesB; tile += npairs)
+      uint32_t use = 0, it = 0;
+      for (int tile = pair; tile < p.tilesB; tile += npairs, ++it) {
+        const uint32_t xcol = (it & 1) ? 256u : 0u, netcol = 256u - xcol;
+        // NET of this tile is the X of the previous one: its head epilogue must have read it
+        if (it > 0 && p.n_post > 0) twait(cx, 4, cx.bar(XP_DONE), (it - 1) & 1, 530);
         for (int j = 0; j < p.n_post; ++j, ++use) {
           gemm_fc0(cx, rb, netcol, use & 1);
           gemm_fc1(cx, rb, xcol, use & 1);
         }
+      }
     }
   } else if (warp >= 4) {
     const Epi e = make_epi(warp, lane);
     const float* biasB = reinterpret_cast<const float*>(p.w + p.off_biasB);
     const float* bias0 = reinterpret_cast<const float*>(p.w + p.off_bias0);
-    uint32_t xph = 0, nph = 0;
-    for (int tile = pair; tile < p.tilesB; tile += npairs) {
-      const long long gp = (long long)tile * 128 + cx.rank * 64 + e.row;
-      const bool valid = gp < p.P;
-      // ---- load pooled x: fp32 -> TMEM residual, relu -> bf16 operand ----
+    // pooled x of `tile`: fp32 -> TMEM residual at column `xc`, relu -> bf16 operand in S_x
+    auto load_x = [&](int tile, uint32_t xc) {
+      const bool valid = (long long)tile * 128 + cx.rank * 64 + e.row < p.P;
+#pragma unroll 1
       for (int nb = 0; nb < 2; ++nb) {
+        const float4* src = reinterpret_cast<const float4*>(p.x3) +
+                            (((((long long)tile * 2 + cx.rank) * 2 + nb) * 2 + e.h) * 32 + e.cs * 16) * 64 + e.row;
+        float4 t[16];  // both 32-column halves in flight: the loads are L2 round trips
+#pragma unroll
+        for (int j = 0; j < 16; ++j) t[j] = valid ? __ldg(src + (size_t)j * 64) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          const float4* src = reinterpret_cast<const float4*>(p.x3) +
-                              (((((long long)tile * 2 + cx.rank) * 2 + nb) * 2 + e.h) * 32 + (e.cs * 16 + half * 8)) * 64 + e.row;
           uint32_t r[32];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float4 t = valid ? __ldg(src + (size_t)j * 64) : make_float4(0.f, 0.f, 0.f, 0.f);
-            r[4 * j] = __float_as_uint(t.x);
-            r[4 * j + 1] = __float_as_uint(t.y);
-            r[4 * j + 2] = __float_as_uint(t.z);
-            r[4 * j + 3] = __float_as_uint(t.w);
+            r[4 * j] = __float_as_uint(t[half * 8 + j].x);
+            r[4 * j + 1] = __float_as_uint(t[half * 8 + j].y);
+            r[4 * j + 2] = __float_as_uint(t[half * 8 + j].z);
+            r[4 * j + 3] = __float_as_uint(t[half * 8 + j].w);
           }
-          tmem_st32(cx.tmem + e.lane_addr + xcol + nb * 128 + e.cs * 64 + half * 32, r);
+          tmem_st32(cx.tmem + e.lane_addr + xc + nb * 128 + e.cs * 64 + half * 32, r);
           const int f0 = feat0(e, nb, half);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -1132,6 +1139,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
         __syncwarp();
         if (p.n_post > 0 && lane == 0) mbar_arrive_cluster(cx.bar(SX_READY + nb * 4 + e.h * 2 + e.cs), 0);
       }
+    };
+    uint32_t xph = 0, nph = 0, it = 0;
+    if (pair < p.tilesB) load_x(pair, 0u);
+    for (int tile = pair; tile < p.tilesB; tile += npairs, ++it) {
+      const uint32_t xcol = (it & 1) ? 256u : 0u, netcol = 256u - xcol;
       for (int j = 0; j < p.n_post; ++j) {
         const int b = p.n_pre + j;
         BiasRegs br;
@@ -1152,6 +1164,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
           xph ^= 1;
         }
       }
+      // NET and S_x are idle from here on (the last fc_0 has been consumed): next tile's x goes there
+      // while the last fc_1 runs
+      if (tile + npairs < p.tilesB) load_x(tile + npairs, netcol);
       // ---- lin_out(relu(x)) + head ----
       const float* bO = biasB + (size_t)p.n_post * DH;
       float part[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1167,6 +1182,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
           uint32_t r[32];
           tmem_ld32(cx.tmem + e.lane_addr + xcol + nb * 128 + e.cs * 64 + half * 32, r);
           tmem_ld_wait();
+          if (nb == 1 && half == 1) {  // X is in registers: the next tile's fc_0 may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(cx.bar(XP_DONE), 0);
+          }
           const int f0 = feat0(e, nb, half);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -1181,7 +1201,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
         }
       }
       if (p.n_post > 0) xph ^= 1;
-      tc_fence_before();
 #pragma unroll
       for (int o = 0; o < 4; ++o) s_part[(o * 4 + e.h * 2 + e.cs) * 64 + e.row] = part[o];
       asm volatile("bar.sync 1, 256;" ::: "memory");
