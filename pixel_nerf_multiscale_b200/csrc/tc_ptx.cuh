@@ -69,6 +69,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the hardware may park the warp for up to `ns` nanoseconds (it is
+// woken as soon as the phase completes), instead of returning after its short default interval.
+// Waiting warps then execute almost no instructions: in the first profile of the fused kernel ~40 %
+// of all executed instructions were this spin loop, which costs clock under the power cap.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must never hang the GPU.  On timeout the barrier id is recorded in
 // *err (global) and the wait returns; the kernel then runs to completion with garbage results and
 // the host reports the failure.
@@ -83,8 +98,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* err, int tag) {
   unsigned long long t0 = 0;
   for (uint32_t it = 1;; ++it) {
-    if (mbar_try_wait(bar, parity)) return;
-    if ((it & 255) == 0) {
+    if (mbar_try_wait_hint(bar, parity, 100000u)) return;
+    if ((it & 15) == 0) {
       if (err && *(volatile int*)err != 0) return;
       unsigned long long now = globaltimer_ns();
       if (t0 == 0) t0 = now;
