@@ -56,6 +56,9 @@ constexpr int KS = 64;                  // K elements per slice
 constexpr int B_CHUNK = 128 * KS * 2;   // 16 KB: [8 k-groups][128 n-rows][8 bf16]
 constexpr int A_SLICE = ROWS * KS * 2;  // 8 KB : [8 k-groups][64 rows][8 bf16]
 constexpr int NB_ST = 6;                // unified operand ring: weight chunks (16 KB) and [latent|code] slices (8 KB)
+#ifndef PNR_RING_A
+#define PNR_RING_A NB_ST                // experiment knob: ring slots phase A actually uses (<= NB_ST); 4/5/6 -> 632k/654k/665k rays/s on C2
+#endif
 constexpr int NB_ST_B = 5;              // phase B: 5 slots, the 6th holds the lin_out weights / partial sums
 constexpr int B_SPLIT = 8;              // TMA boxes per weight chunk (2 KB each: small boxes land sooner)
 constexpr int A_SPLIT = 4;              // TMA boxes per operand slice
@@ -885,7 +888,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
     // ===================== producer (whole warp, uniform control flow) =====================
     {
       Ring rb;
-      rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST);
+      rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), PNR_RING_A);
       uint32_t git = 0;
       for (int tile = pair; tile < p.tilesA; tile += npairs, ++git) {
         if (p.fused_gather) {  // this CTA's rows of the tile have been gathered (and are visible to TMA)
@@ -924,7 +927,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
     // ===================== MMA issuer: leader CTA only, whole warp, uniform control flow ======
     if (cx.rank == 0) {
       Ring rb;
-      rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST);
+      rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), PNR_RING_A);
       uint32_t use = 0;  // (tile-local block counter) parity source for SX/H barriers
       uint32_t it = 0;
       for (int tile = pair; tile < p.tilesA; tile += npairs, ++it) {

@@ -238,6 +238,13 @@ class PixelNeRFNet(torch.nn.Module):
         return out
 
     # ------------------------------------------------------------------------------------------
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """Accepts the model's own keys, the fork trainer's checkpoint dict, DataParallel saves and
+        upstream pixelNeRF checkpoints (model/checkpoint.py)."""
+        from .checkpoint import normalize_state_dict
+
+        return super().load_state_dict(normalize_state_dict(state_dict, self.state_dict()), strict=strict, **kw)
+
     def load_weights(self, args, opt_init=False, strict=True, device=None):
         """Loads checkpoints/<name>/pixel_nerf_{latest,init} like the reference
         (models.py.backup2:284-314); returns self."""

@@ -2,6 +2,7 @@
 loud failure without CUDA.  CPU only."""
 import math
 import os
+import types
 
 import pytest
 import torch
@@ -129,3 +130,42 @@ def test_util_rays():
     assert torch.allclose(rays[..., 3:6].norm(dim=-1), torch.ones(1, 6, 8), atol=1e-6)
     assert torch.allclose(rays[..., :3], poses[0, :3, 3].expand(1, 6, 8, 3)) and rays[..., 6].eq(0.5).all()
     assert math.isclose(pk.util.psnr(torch.zeros(4), torch.full((4,), 0.1)), 20.0, rel_tol=1e-5)
+
+
+def test_checkpoint_compatibility(tmp_path):
+    """trainer dicts, DataParallel prefixes and upstream pixelNeRF files load strictly."""
+    from pixel_nerf_multiscale_b200.model.checkpoint import normalize_state_dict
+
+    conf = pk.util.conf.ConfigFactory.parse_file(os.path.join(REPO, "conf/exp/sn64.conf"))
+    conf.put("model.encoder.pretrained", False)
+    torch.manual_seed(0)
+    src = pk.make_model(conf["model"])
+    sd = src.state_dict()
+    assert any(k.startswith("encoder.layers.") for k in sd)  # the fork's aliases of encoder.model.layerN
+    upstream = {k: v for k, v in sd.items() if not k.startswith("encoder.layers.")}
+    upstream["poses"] = torch.zeros(1, 3, 4)       # transient buffers some upstream versions saved
+    upstream["encoder.latent"] = torch.zeros(1, 1, 1, 1)
+    variants = {
+        "own": sd,
+        "upstream": upstream,
+        "trainer": {"epoch": 3, "iter": 10, "net_state_dict": sd, "optimizer_state_dict": {}},
+        "dataparallel": {"module." + k: v for k, v in upstream.items()},
+    }
+    for name, obj in variants.items():
+        torch.manual_seed(1)
+        dst = pk.make_model(conf["model"])
+        res = dst.load_state_dict(obj, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys, name
+        for k, v in dst.state_dict().items():
+            assert torch.equal(v, sd[k]), (name, k)
+    # load_weights reads the same formats from checkpoints/<name>/pixel_nerf_latest
+    os.makedirs(tmp_path / "exp")
+    torch.save(variants["trainer"], tmp_path / "exp" / "pixel_nerf_latest")
+    args = types.SimpleNamespace(checkpoints_path=str(tmp_path), name="exp", resume=True)
+    dst = pk.make_model(conf["model"]).load_weights(args)
+    assert torch.equal(dst.mlp_coarse.lin_out.weight, src.mlp_coarse.lin_out.weight)
+    # latent-width mismatch names the conf switch
+    bad = dict(sd)
+    bad["mlp_coarse.lin_z.0.weight"] = torch.zeros(512, 512)
+    with pytest.raises(RuntimeError, match="use_multi_scale"):
+        normalize_state_dict(bad, sd)

@@ -9,7 +9,10 @@
 #include <cstdio>
 #include <cstdlib>
 
-constexpr int CHUNK = 16384, STAGES = 6;
+#ifndef STAGES
+#define STAGES 6
+#endif
+constexpr int CHUNK = 16384;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(n)); }
