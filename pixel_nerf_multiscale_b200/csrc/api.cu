@@ -1,5 +1,6 @@
 // extern "C" surface declared in include/pixelnerf_b200.h + host-side orchestration of one
 // PixelNeRFNet.forward (models.py.backup2:155-282) and one NeRFRenderer.forward (nerf.py:251-303).
+#include <cstdlib>
 #include <stdarg.h>
 
 #include <vector>
@@ -116,8 +117,16 @@ static pnr_scene object_scene(const pnr_scene& sc, int sb) {
   return s;
 }
 
+static long long bf16_chunk_rows() {
+  static long long rows = [] {  // PNR_CHUNK_ROWS_LOG2: experiment knob (scratch grows with it)
+    const char* e = getenv("PNR_CHUNK_ROWS_LOG2");
+    int l = e ? atoi(e) : 0;
+    return (l >= 14 && l <= 26) ? (1LL << l) : kChunkRowsBF16;
+  }();
+  return rows;
+}
 static long long chunk_points(const pnr_scene& sc, int precision, int K, long long P) {
-  long long rows = precision == PNR_FP32 ? kChunkRowsF32 : kChunkRowsBF16;
+  long long rows = precision == PNR_FP32 ? kChunkRowsF32 : bf16_chunk_rows();
   long long pts = rows / sc.ns;
   if (K > 0) pts = (pts / K) * K;  // whole rays only
   if (pts < (K > 0 ? K : 1)) pts = (K > 0 ? K : 1);
