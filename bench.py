@@ -163,11 +163,12 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, pw = [], None, set(), []
         for s in self.samples:
             try:
                 sm.append(float(s[0]))
                 mx = float(s[1])
+                pw.append(float(s[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
@@ -175,8 +176,9 @@ class ClockSampler:
                 pass
         sm.sort()
         busy = [x for x in sm if mx and x > 0.5 * mx] or sm
+        pw.sort()
         return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_median": pw[len(pw) // 2] if pw else None, "power_w_max": pw[-1] if pw else None}
 
 
 def main():
