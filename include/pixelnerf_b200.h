@@ -167,6 +167,15 @@ int pnr_gen_rays(const float* poses_c2w, int N, int W, int H, float fx, float fy
  * src/util/util.py:479-486) without the per-batch .cpu() sync of the reference. */
 int pnr_finalize_rgb(const float* rgb, const float* gt, int64_t n, uint8_t* u8, double* sse, pnr_stream stream);
 
+/* Per-view metrics of the eval driver (eval/eval.py:314-343) on (NV,H,W,C) fp32 images, rgb clamped to [0,1]
+ * first (eval.py:290-292): sums[2*v] += SSIM map summed over the cropped interior and channels as
+ * skimage.measure.compare_ssim(multichannel=True, data_range) defines it (third-party, absent from the
+ * reference tree: scikit-image 0.16 structural_similarity, uniform win x win window, sample covariance,
+ * K1 = 0.01, K2 = 0.03) -- divide by C*(H-win+1)*(W-win+1); sums[2*v+1] += sum of squared error for
+ * compare_psnr = 10 log10(R^2 / mse) -- divide by H*W*C.  sums is fp64, caller-zeroed; no host sync. */
+int pnr_frame_metrics(const float* rgb, const float* gt, int NV, int H, int W, int C, int win, float data_range,
+                      double* sums, pnr_stream stream);
+
 /* ---- kernel (c): per-ray sampling / compositing (src/render/nerf.py) ------------------ */
 /* sample_coarse, nerf.py:98-118.  rays (B,8), jitter (B,Kc) -> z (B,Kc).                 */
 int pnr_sample_coarse(const float* rays, const float* jitter, int B, int Kc, int lindisp,

@@ -458,3 +458,37 @@ def gen_rays(poses, width, height, focal, z_near, z_far, c=None):
     near = torch.full((N, height, width, 1), float(z_near), device=dev)
     far = torch.full((N, height, width, 1), float(z_far), device=dev)
     return torch.cat((cen, dirs, near, far), dim=-1)
+
+
+# ---- per-view metrics of the eval driver (eval/eval.py:314-343) -------------------------------------
+# The reference calls skimage.measure.compare_ssim / compare_psnr (scikit-image, NOT vendored in
+# /root/reference and not installed here; the `compare_*` names exist up to scikit-image 0.17, no
+# version is pinned by the reference).  Restated from the published algorithm of
+# skimage.metrics.structural_similarity (Wang et al. 2004 with skimage's defaults): per channel,
+# float64, uniform win x win filter, sample covariance (NP/(NP-1)), K1=0.01, K2=0.03, mean of the
+# SSIM map with a (win-1)//2 border cropped; multichannel = mean over channels.  compare_psnr =
+# 10 log10(data_range^2 / mse).  No golden vector exists in the reference for these ("parity
+# unpinned" for this function); tests pin the restatement against a brute-force window loop.
+def frame_metrics(rgb, gt, data_range=1.0, win=7):
+    """rgb, gt (H,W,C) arrays/tensors; rgb is clamped to [0,1] first (eval.py:290-292).
+    :return (psnr, ssim) python floats"""
+    import numpy as np
+    from scipy.ndimage import uniform_filter
+
+    a = np.clip(np.asarray(rgb, dtype=np.float32), 0.0, 1.0).astype(np.float64)
+    b = np.asarray(gt, dtype=np.float32).astype(np.float64)
+    mse = np.mean((a - b) ** 2)
+    psnr = 10.0 * np.log10(data_range ** 2 / mse)
+    npix = win * win
+    cov_norm = npix / (npix - 1.0)
+    c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    pad = (win - 1) // 2
+    vals = []
+    for ch in range(a.shape[2]):
+        x, y = a[..., ch], b[..., ch]
+        ux, uy = uniform_filter(x, size=win), uniform_filter(y, size=win)
+        uxx, uyy, uxy = uniform_filter(x * x, size=win), uniform_filter(y * y, size=win), uniform_filter(x * y, size=win)
+        vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+        s = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux ** 2 + uy ** 2 + c1) * (vx + vy + c2))
+        vals.append(s[pad:-pad, pad:-pad].mean())
+    return float(psnr), float(np.mean(vals))

@@ -79,6 +79,7 @@ EXPORTS = {
     "pnr_mlp_forward": (_i, [_PM, _fp, _i, _i, _i, _i, _fp, _fp, _sz, _fp]),
     "pnr_gen_rays": (_i, [_fp, _i, _i, _i, _f, _f, _f, _f, _f, _f, _fp, _fp]),
     "pnr_finalize_rgb": (_i, [_fp, _fp, C.c_int64, _fp, _fp, _fp]),
+    "pnr_frame_metrics": (_i, [_fp, _fp, _i, _i, _i, _i, _i, _f, _fp, _fp]),
     "pnr_sample_coarse": (_i, [_fp, _fp, _i, _i, _i, _fp, _fp]),
     "pnr_composite": (_i, [_fp, _fp, _fp, _i, _i, _i, _fp, _fp, _fp, _fp]),
     "pnr_fine_indices": (_i, [_fp, _fp, _i, _i, _i, _fp, _fp]),

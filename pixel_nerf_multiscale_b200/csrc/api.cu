@@ -305,6 +305,15 @@ int pnr_finalize_rgb(const float* rgb, const float* gt, int64_t n, uint8_t* u8, 
   return launch_finalize_rgb(rgb, gt, n, u8, sse, (cudaStream_t)stream);
 }
 
+int pnr_frame_metrics(const float* rgb, const float* gt, int NV, int H, int W, int C, int win, float data_range,
+                      double* sums, pnr_stream stream) {
+  PNR_CHECK_ARG(rgb && gt && sums, "frame_metrics: NULL pointer");
+  PNR_CHECK_ARG(NV >= 0 && H >= 1 && W >= 1 && C >= 1, "frame_metrics: bad image shape (%d,%d,%d,%d)", NV, H, W, C);
+  PNR_CHECK_ARG(win >= 3 && (win & 1) == 1 && win <= H && win <= W, "frame_metrics: win=%d must be odd, >= 3 and fit the image", win);
+  PNR_CHECK_ARG(data_range > 0.f, "frame_metrics: data_range must be positive");
+  return launch_frame_metrics(rgb, gt, NV, H, W, C, win, data_range, sums, (cudaStream_t)stream);
+}
+
 int pnr_sample_coarse(const float* rays, const float* jitter, int B, int Kc, int lindisp, float* z, pnr_stream stream) {
   PNR_CHECK_ARG(rays && jitter && z, "sample_coarse: NULL pointer");
   PNR_CHECK_ARG(Kc >= 1, "sample_coarse: Kc must be >= 1");

@@ -101,6 +101,8 @@ int launch_sample_coarse(const float* rays, const float* jitter, int B, int Kc, 
                          cudaStream_t st);
 int launch_gen_rays(const float* poses, int N, int W, int H, float fx, float fy, float cx, float cy, float near,
                     float far, float* rays, cudaStream_t st);
+int launch_frame_metrics(const float* a, const float* b, int NV, int H, int W, int C, int win, float data_range,
+                         double* sums, cudaStream_t st);
 int launch_finalize_rgb(const float* rgb, const float* gt, long long n, uint8_t* u8, double* sse, cudaStream_t st);
 int launch_composite(const float* rays, const float* z, const float* rgb_sigma, int B, int K, int white,
                      float* weights, float* rgb, float* depth, cudaStream_t st);

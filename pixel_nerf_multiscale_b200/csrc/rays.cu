@@ -115,6 +115,71 @@ int launch_finalize_rgb(const float* rgb, const float* gt, long long n, uint8_t*
   return PNR_OK;
 }
 
+// ---- per-view image metrics (eval/eval.py:314-343) --------------------------------------------------
+// SSIM as skimage.measure.compare_ssim(a, b, multichannel=True, data_range=R) computes it (defaults:
+// 7x7 uniform window, sample covariance, K1 = 0.01, K2 = 0.03; per channel, mean over the image with
+// the (win-1)/2 border cropped, then mean over channels), and the squared error for compare_psnr.
+// Images are (NV,H,W,C) fp32; a is clamped to [0,1] first like the driver does.  One thread per
+// interior pixel and channel, fp64 window sums (the variance is a difference of nearly equal
+// numbers), block reduction, one atomicAdd per block into sums[view*2 + {0: ssim, 1: sq. error}].
+__global__ void __launch_bounds__(256)
+frame_metrics_kernel(const float* __restrict__ a, const float* __restrict__ b, int H, int W, int C, int win,
+                     double c1, double c2, double* __restrict__ sums) {
+  const int view = blockIdx.y;
+  const int pad = (win - 1) / 2;
+  const int Hi = H - 2 * pad, Wi = W - 2 * pad;
+  const long long n_in = (long long)(Hi > 0 ? Hi : 0) * (Wi > 0 ? Wi : 0) * C;
+  const long long n_all = (long long)H * W * C;
+  const float* av = a + (size_t)view * n_all;
+  const float* bv = b + (size_t)view * n_all;
+  double ssim = 0.0, se = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_all; i += (long long)gridDim.x * blockDim.x) {
+    const float d = fminf(fmaxf(av[i], 0.f), 1.f) - bv[i];
+    se += (double)d * (double)d;
+    if (i < n_in) {
+      const int c = (int)(i % C);
+      const int x = (int)((i / C) % Wi), y = (int)(i / ((long long)C * Wi));
+      double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+      for (int dy = 0; dy < win; ++dy) {
+        const size_t row = ((size_t)(y + dy) * W + x) * C + c;
+        for (int dx = 0; dx < win; ++dx) {
+          const double p = (double)fminf(fmaxf(av[row + (size_t)dx * C], 0.f), 1.f), q = (double)bv[row + (size_t)dx * C];
+          sx += p; sy += q; sxx += p * p; syy += q * q; sxy += p * q;
+        }
+      }
+      const double np = (double)win * win, cov = np / (np - 1.0);
+      const double ux = sx / np, uy = sy / np;
+      const double vx = cov * (sxx / np - ux * ux), vy = cov * (syy / np - uy * uy), vxy = cov * (sxy / np - ux * uy);
+      ssim += ((2.0 * ux * uy + c1) * (2.0 * vxy + c2)) / ((ux * ux + uy * uy + c1) * (vx + vy + c2));
+    }
+  }
+  __shared__ double sh[2][8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ssim += __shfl_xor_sync(0xffffffffu, ssim, o);
+    se += __shfl_xor_sync(0xffffffffu, se, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = ssim; sh[1][threadIdx.x >> 5] = se; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
+    atomicAdd(&sums[(size_t)view * 2 + threadIdx.x], t);
+  }
+}
+
+int launch_frame_metrics(const float* a, const float* b, int NV, int H, int W, int C, int win, float data_range,
+                         double* sums, cudaStream_t st) {
+  if (NV == 0) return PNR_OK;
+  const long long n_all = (long long)H * W * C;
+  unsigned bx = (unsigned)ceil_div_ll(n_all, 256);
+  if (bx > 2048) bx = 2048;
+  const double c1 = (0.01 * data_range) * (0.01 * data_range), c2 = (0.03 * data_range) * (0.03 * data_range);
+  frame_metrics_kernel<<<dim3(bx, (unsigned)NV), 256, 0, st>>>(a, b, H, W, C, win, c1, c2, sums);
+  PNR_LAUNCHED();
+  return PNR_OK;
+}
+
 // ---- composite --------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

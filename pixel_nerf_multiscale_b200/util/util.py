@@ -94,6 +94,31 @@ def psnr(pred, target):
     return -10 * math.log10(mse)
 
 
+def frame_metrics(rgb, target, data_range=1.0, win_size=7):
+    """Per-view PSNR and SSIM of rendered frames against ground truth, on the device and without a
+    host sync -- what eval/eval.py:314-343 computes per view with skimage's compare_psnr /
+    compare_ssim(multichannel=True, data_range=1) after clamping the render to [0,1].
+    :param rgb, target (NV,H,W,C) or (H,W,C) CUDA tensors
+    :return (psnr (NV,), ssim (NV,)) fp64 device tensors"""
+    from .. import _native as N
+
+    if not rgb.is_cuda:
+        raise RuntimeError("pixelnerf_b200: frame_metrics needs CUDA tensors")
+    x = rgb.detach().float().contiguous()
+    gt = target.detach().float().contiguous().to(x.device)
+    assert x.shape == gt.shape and x.dim() in (3, 4)
+    if x.dim() == 3:
+        x, gt = x[None], gt[None]
+    NV, H, W, Cc = x.shape
+    sums = torch.zeros(NV, 2, dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        N.check(N.lib().pnr_frame_metrics(N.ptr(x), N.ptr(gt), NV, H, W, Cc, int(win_size), float(data_range),
+                                          N.ptr(sums), N.stream_ptr(x.device)), "pnr_frame_metrics")
+    ssim = sums[:, 0] / float(Cc * (H - win_size + 1) * (W - win_size + 1))
+    mse = sums[:, 1] / float(H * W * Cc)
+    return 10.0 * torch.log10(float(data_range) ** 2 / mse), ssim
+
+
 def finalize_frames(rgb, target=None):
     """Device-side tail of the eval drivers: clamp to [0,1], quantise to uint8 (what gen_video writes)
     and, with a ground-truth image, PSNR of the clamped frame -- all without a host sync.

@@ -3,6 +3,8 @@ GPU parity, fp32 validation mode: the CUDA path (through the C ABI) against the 
 same device and against the reference-generated goldens.  Tolerance (BASELINE.json north_star):
 per-pixel RGB/depth max-abs <= 1e-4 in fp32 mode.
 """
+import math
+
 import pytest
 import torch
 
@@ -180,3 +182,26 @@ def test_finalize_frames_on_device():
     assert abs(psnr.item() - ref_psnr) < 1e-6
     u8b, none = pk.util.finalize_frames(rgb.cuda())
     assert none is None and torch.equal(u8b, u8)
+
+
+def test_frame_metrics_on_device():
+    """per-view PSNR / SSIM of the eval driver (eval/eval.py:314-343) on the device vs the
+    fp64 restatement of skimage's compare_psnr / compare_ssim; fp64 window sums -> 1e-9."""
+    import pixel_nerf_multiscale_b200 as pk
+
+    g = torch.Generator().manual_seed(11)
+    NV, H, W = 3, 37, 52
+    gt = torch.rand(NV, H, W, 3, generator=g)
+    rgb = gt + 0.08 * torch.randn(NV, H, W, 3, generator=g)  # partly outside [0,1]
+    rgb[2] = gt[2]                                           # identical view: ssim 1, psnr inf
+    psnr, ssim = pk.util.frame_metrics(rgb.cuda(), gt.cuda())
+    assert psnr.shape == (NV,) and ssim.shape == (NV,) and psnr.dtype == torch.float64
+    for v in range(2):
+        rp, rs = po.frame_metrics(rgb[v].numpy(), gt[v].numpy())
+        assert abs(psnr[v].item() - rp) < 1e-9 and abs(ssim[v].item() - rs) < 1e-9, (v, psnr[v].item(), rp, ssim[v].item(), rs)
+    assert math.isinf(psnr[2].item()) and abs(ssim[2].item() - 1.0) < 1e-12
+    # single image form + loud argument errors
+    p1, s1 = pk.util.frame_metrics(rgb[0].cuda(), gt[0].cuda())
+    assert torch.equal(p1, psnr[:1]) and abs(s1.item() - ssim[0].item()) < 1e-12  # atomics order may differ in the last bit
+    with pytest.raises(AssertionError):
+        pk.util.frame_metrics(torch.rand(1, 5, 5, 3).cuda(), torch.rand(1, 5, 5, 3).cuda())  # 7x7 window does not fit

@@ -5,6 +5,8 @@ Tolerances: fp32 restatement vs fp32 reference on the same CPU build -> 2e-5 abs
 quantities (summation order inside addmm / cumprod may differ), indices and sample
 positions essentially exact.
 """
+import math
+
 import pytest
 import torch
 
@@ -80,3 +82,30 @@ def test_positional_encoding_layout():
     assert torch.allclose(e[0, 3:6], torch.sin(1.5 * x[0]), atol=1e-6)
     assert torch.allclose(e[0, 6:9], torch.cos(1.5 * x[0]), atol=1e-6)
     assert torch.allclose(e[0, 9:12], torch.sin(3.0 * x[0]), atol=1e-6)
+
+
+def test_frame_metrics_restatement():
+    """SSIM/PSNR restatement (skimage is absent): brute-force window loop on a small image + invariants."""
+    import numpy as np
+
+    rng = np.random.default_rng(0)
+    H, W, C, win = 12, 11, 3, 7
+    gt = rng.random((H, W, C)).astype(np.float32)
+    img = (gt + 0.1 * rng.standard_normal((H, W, C))).astype(np.float32)  # leaves [0,1]: exercises the clamp
+    psnr, ssim = po.frame_metrics(img, gt)
+    a = np.clip(img, 0, 1).astype(np.float64)
+    b = gt.astype(np.float64)
+    acc = []
+    for c in range(C):
+        for y in range(H - win + 1):
+            for x in range(W - win + 1):
+                p, q = a[y:y + win, x:x + win, c].ravel(), b[y:y + win, x:x + win, c].ravel()
+                ux, uy = p.mean(), q.mean()
+                vx, vy = p.var(ddof=1), q.var(ddof=1)
+                vxy = ((p - ux) * (q - uy)).sum() / (win * win - 1)
+                acc.append(((2 * ux * uy + 1e-4) * (2 * vxy + 9e-4)) / ((ux * ux + uy * uy + 1e-4) * (vx + vy + 9e-4)))
+    assert abs(ssim - float(np.mean(acc))) < 1e-12
+    assert abs(psnr - 10 * math.log10(1.0 / np.mean((a - b) ** 2))) < 1e-12
+    assert abs(po.frame_metrics(gt, gt + 0.0)[1] - 1.0) < 1e-12       # identical images
+    const = np.full((9, 9, 1), 0.5, np.float32)
+    assert abs(po.frame_metrics(const, const - 0.1)[0] - 20.0) < 1e-5  # mse = 0.01
