@@ -56,6 +56,48 @@ def gather_outputs(t, total, dim=1, group=None):
     return torch.cat([p.narrow(dim, 0, hi - lo) for p, (lo, hi) in zip(parts, sizes)], dim=dim)
 
 
+def render_views(render_par, poses, width, height, focal, z_near, z_far, c=None, ray_batch_size=50000,
+                 rank=None, world=None, gather=True, group=None):
+    """The frame loop of the reference's drivers (eval/gen_video.py:174-237, eval/eval.py:250-292)
+    with the rays generated where they are rendered: every rank derives ITS contiguous
+    range of the NV*H*W rays from (poses, focal, c) -- no (NV,H,W,8) host tensor, no scatter --
+    renders it in ``ray_batch_size`` batches through ``render_par`` (``bind_parallel(...,
+    simple_output=True)``) and, with ``gather``, all ranks receive the whole frames.
+
+    :param poses (NV,4,4) camera-to-world on the rendering device
+    :return rgb (NV,H,W,3), depth (NV,H,W); without ``gather`` this rank's flat slices
+            (n,3), (n,) and its [lo, hi) ray range
+    """
+    from . import util
+
+    distributed = dist.is_available() and dist.is_initialized()
+    if rank is None:
+        rank = dist.get_rank(group) if distributed else 0
+    if world is None:
+        world = dist.get_world_size(group) if distributed else 1
+    nv, per_frame = poses.shape[0], width * height
+    total = nv * per_frame
+    lo, hi = shard_bounds(total, rank, world)
+    rgb_parts, depth_parts = [], []
+    if hi > lo:
+        f0, f1 = lo // per_frame, (hi - 1) // per_frame + 1   # frames this range touches
+        rays = util.gen_rays(poses[f0:f1], width, height, focal, z_near, z_far, c=c).reshape(-1, 8)
+        rays = rays[lo - f0 * per_frame: hi - f0 * per_frame]
+        for batch in torch.split(rays, ray_batch_size, dim=0):
+            rgb, depth = render_par(batch[None])
+            rgb_parts.append(rgb[0])
+            depth_parts.append(depth[0])
+    dev = poses.device
+    rgb = torch.cat(rgb_parts) if rgb_parts else torch.zeros(0, 3, device=dev)
+    depth = torch.cat(depth_parts) if depth_parts else torch.zeros(0, device=dev)
+    if not gather:
+        return rgb, depth, (lo, hi)
+    if world > 1:
+        rgb = gather_outputs(rgb.contiguous(), total, dim=0, group=group)
+        depth = gather_outputs(depth.contiguous(), total, dim=0, group=group)
+    return rgb.reshape(nv, height, width, 3), depth.reshape(nv, height, width)
+
+
 def broadcast_scene(net, src=0, group=None):
     """Make every rank's PixelNeRFNet hold rank `src`'s encoded source views and MLP weights.
     Call after ``net.encode`` on `src` (other ranks need not have encoded anything)."""

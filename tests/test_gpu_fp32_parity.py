@@ -205,3 +205,25 @@ def test_frame_metrics_on_device():
     assert torch.equal(p1, psnr[:1]) and abs(s1.item() - ssim[0].item()) < 1e-12  # atomics order may differ in the last bit
     with pytest.raises(AssertionError):
         pk.util.frame_metrics(torch.rand(1, 5, 5, 3).cuda(), torch.rand(1, 5, 5, 3).cuda())  # 7x7 window does not fit
+
+
+def test_render_views_generates_rays_on_device():
+    """the frame loop with per-rank on-device ray generation equals rendering the same
+    rays passed in explicitly (same torch RNG stream, one batch per frame)."""
+    import pixel_nerf_multiscale_b200 as pk
+    from pixel_nerf_multiscale_b200.parallel import render_views
+
+    net, conf, scene, raw = build_product("ss_ns1", precision="fp32")
+    renderer = make_renderer(conf, {})
+    par = renderer.bind_parallel(net, [0], simple_output=True).eval()
+    W, H = 12, 10
+    poses = torch.stack([pk.util.pose_spherical(25.0 * i, -15.0, 2.6) for i in range(2)]).cuda()
+    torch.manual_seed(5)
+    rgb, depth = render_views(par, poses, W, H, 60.0, 1.2, 4.0, ray_batch_size=W * H)
+    assert rgb.shape == (2, H, W, 3) and depth.shape == (2, H, W)
+    rays = pk.util.gen_rays(poses, W, H, 60.0, 1.2, 4.0).reshape(2, W * H, 8)
+    torch.manual_seed(5)
+    for f in range(2):
+        r, d = par(rays[f][None])
+        assert torch.equal(r[0], rgb[f].reshape(-1, 3)) and torch.equal(d[0], depth[f].reshape(-1))
+    assert torch.isfinite(rgb).all() and float(depth.min()) >= 0.0

@@ -33,7 +33,19 @@ def _worker(rank, world, port, q):
     rays = torch.arange(1 * 11 * 8, dtype=torch.float32).reshape(1, 11, 8)
     mine = shard_rays(rays)
     back = gather_outputs(mine[..., :3].contiguous(), 11)
-    q.put((rank, sig, mine.shape[1], torch.equal(back, rays[..., :3])))
+    # render_views: each rank generates and "renders" only its own ray range; frames come back whole
+    from pixel_nerf_multiscale_b200.parallel import render_views
+
+    def fake_render(r):  # deterministic function of the ray record, shapes of _RenderWrapper(simple_output=True)
+        return r[..., 3:6] * 0.5 + r[..., :3], r[..., 6] + r[..., 3]
+
+    vposes = torch.stack([pk.util.pose_spherical(40.0 * i, -10.0, 2.0) for i in range(3)])
+    rgb, depth = render_views(fake_render, vposes, 7, 5, 30.0, 0.5, 3.0, ray_batch_size=13)
+    full = pk.util.gen_rays(vposes, 7, 5, 30.0, 0.5, 3.0)
+    exp_rgb, exp_depth = fake_render(full)
+    frames_ok = rgb.shape == (3, 5, 7, 3) and torch.equal(rgb, exp_rgb) and torch.equal(depth, exp_depth)
+    _, _, (lo, hi) = render_views(fake_render, vposes, 7, 5, 30.0, 0.5, 3.0, gather=False)
+    q.put((rank, sig, mine.shape[1], torch.equal(back, rays[..., :3]) and frames_ok and (hi - lo) in (52, 53)))
     dist.destroy_process_group()
 
 
