@@ -21,6 +21,7 @@
 // Phase B (rows = points): remaining blocks, lin_out, sigmoid/relu head (models.py.backup2:274-281).
 // Every mbarrier wait is wall-clock bounded; a protocol fault writes its tag to pinned host memory
 // and traps (pnr_tc_check reports it) instead of hanging the GPU.
+#include <cstdlib>
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -1197,9 +1198,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
             const float xs[4] = {fmaxf(__uint_as_float(r[4 * j + 0]) + bb.x, 0.f), fmaxf(__uint_as_float(r[4 * j + 1]) + bb.y, 0.f),
                                  fmaxf(__uint_as_float(r[4 * j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(r[4 * j + 3]) + bb.w, 0.f)};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-              for (int o = 0; o < 4; ++o) part[o] = fmaf(xs[i], s_wout[o * DH + f0 + 4 * j + i], part[o]);
+            for (int o = 0; o < 4; ++o) {  // one 128-bit broadcast read per (output, 4 features)
+              const float4 w4 = *reinterpret_cast<const float4*>(s_wout + o * DH + f0 + 4 * j);
+              part[o] = fmaf(xs[0], w4.x, part[o]);
+              part[o] = fmaf(xs[1], w4.y, part[o]);
+              part[o] = fmaf(xs[2], w4.z, part[o]);
+              part[o] = fmaf(xs[3], w4.w, part[o]);
+            }
           }
         }
       }
@@ -1312,6 +1317,8 @@ static int num_pairs(int tiles) {
     if (sms <= 0) sms = 148;
   }
   int pairs = sms / 2;
+  static int cap = [] { const char* e = getenv("PNR_MAX_PAIRS"); return e ? atoi(e) : 0; }();  // experiment knob
+  if (cap > 0 && cap < pairs) pairs = cap;
   return tiles < pairs ? tiles : pairs;
 }
 

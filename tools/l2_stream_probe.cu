@@ -22,7 +22,7 @@ __device__ __forceinline__ void mbar_expect(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
   for (unsigned spins = 0; !ok; ++spins) {
-    if (spins > (1u << 24)) __trap();  // a protocol bug must not hang the box
+    if (spins > (1u << 28)) __trap();  // a protocol bug must not hang the box
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   }
@@ -135,6 +135,13 @@ int main(int argc, char** argv) {
   cudaMalloc(&w, wbytes); cudaMemset(w, 1, wbytes); cudaMalloc(&sink, 8);
   int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   printf("SMs %d, image %zu KB, passes %d\n", sms, wbytes / 1024, passes);
+  if (argc > 3) {  // power mode: one configuration, long enough for nvidia-smi to sample
+    const int which = atoi(argv[3]);
+    if (which == 0) run<1>("unicast lockstep", w, wbytes, passes, 0, sms, sink);
+    if (which == 1) run<4>("cluster 4 multicast", w, wbytes, passes, 2, sms, sink);
+    if (which == 2) run<2>("cluster 2 multicast", w, wbytes, passes, 2, sms, sink);
+    return cudaDeviceSynchronize() != cudaSuccess;
+  }
   run<1>("unicast lockstep", w, wbytes, passes, 0, sms, sink);
   run<1>("unicast skewed", w, wbytes, passes, 1, sms, sink);
   run<2>("cluster 2 unicast skewed", w, wbytes, passes, 1, sms, sink);
