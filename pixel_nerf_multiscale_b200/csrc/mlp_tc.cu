@@ -61,8 +61,14 @@ constexpr int NB_ST = 6;                // unified operand ring: weight chunks (
 #define PNR_RING_A NB_ST                // experiment knob: ring slots phase A actually uses (<= NB_ST); 4/5/6 -> 632k/654k/665k rays/s on C2
 #endif
 constexpr int NB_ST_B = 5;              // phase B: 5 slots, the 6th holds the lin_out weights / partial sums
-constexpr int B_SPLIT = 8;              // TMA boxes per weight chunk (2 KB each: small boxes land sooner)
-constexpr int A_SPLIT = 4;              // TMA boxes per operand slice
+#ifndef PNR_B_SPLIT
+#define PNR_B_SPLIT 2
+#endif
+#ifndef PNR_A_SPLIT
+#define PNR_A_SPLIT 1
+#endif
+constexpr int B_SPLIT = PNR_B_SPLIT;    // TMA boxes per weight chunk (8/4/2/1 -> 667/671/673/673 k rays/s on C2)
+constexpr int A_SPLIT = PNR_A_SPLIT;    // TMA boxes per operand slice
 constexpr int OFF_SX = 0;
 constexpr int OFF_H = OFF_SX + ROWS * DH * 2;
 constexpr int OFF_BRING = OFF_H + ROWS * DH * 2;
