@@ -532,6 +532,23 @@ rows_to_operand_kernel(const float* __restrict__ zx, int d_latent, int d_in, int
 // =============================================================================================
 // the fused MLP kernels
 // =============================================================================================
+// Producer and MMA-issuer roles: run by ONE elected thread for the whole role (PNR_SOLO_ROLES=1) instead of
+// the whole warp electing a lane around every instruction: the per-chunk control path (BRA.DIV / BSSY /
+// ELECT / R2UR) was the bound of both kernels -- with a quarter of the tensor work AND a quarter of the
+// weight traffic a tile still took 96 % of its cycles.
+#ifndef PNR_SOLO_ROLES
+#define PNR_SOLO_ROLES 1
+#endif
+#if PNR_SOLO_ROLES
+#define ROLE_ELECT() true
+#define ROLE_SYNC() ((void)0)
+#define ROLE_ENTER() elect_one()
+#else
+#define ROLE_ELECT() elect_one()
+#define ROLE_SYNC() __syncwarp()
+#define ROLE_ENTER() true
+#endif
+
 struct Ring {
   uint32_t full, empty;  // smem addresses of barrier arrays
   int n, idx;
@@ -579,28 +596,34 @@ __device__ __forceinline__ void load_b(Ctx& cx, Ring& rb, const CUtensorMap* tm,
 #endif
   const int row0 = (int)(byte_off >> 8);
   const uint32_t dst = cx.smem + OFF_BRING + rb.idx * B_CHUNK, fb = rb.full_bar();
-  if (elect_one()) {  // operands computed in warp-uniform code -> uniform registers, no R2UR waterfall
+  if (ROLE_ELECT()) {  // operands computed in warp-uniform code -> uniform registers, no R2UR waterfall
+#ifdef PNR_EXP_NOLOAD  // timing experiment: a quarter of the weight traffic (results are garbage)
+    if (cx.rank == 0) mbar_expect_tx(fb, 2 * (B_CHUNK / 4));
+    for (int q = 0; q < B_SPLIT / 4; ++q)
+      tma_load_2d_pair(dst + q * (B_CHUNK / B_SPLIT), tm, 0, row0 + q * (B_CHUNK / B_SPLIT / 256), fb);
+#else
     if (cx.rank == 0) mbar_expect_tx(fb, 2 * B_CHUNK);
 #pragma unroll
     for (int q = 0; q < B_SPLIT; ++q)
       tma_load_2d_pair(dst + q * (B_CHUNK / B_SPLIT), tm, 0, row0 + q * (B_CHUNK / B_SPLIT / 256), fb);
+#endif
 #if PNR_TC_STATS
     *(volatile long long*)ts_slot(0, rb.idx) = clock64();
 #endif
   }
-  __syncwarp();
+  ROLE_SYNC();
   rb.advance();
 }
 __device__ __forceinline__ void load_a(Ctx& cx, Ring& ra, const CUtensorMap* tm, size_t byte_off) {
   twait(cx, 1, ra.empty_bar(), ra.phase ^ 1, 202);
   const uint32_t dst = cx.smem + OFF_BRING + ra.idx * B_CHUNK, fb = ra.full_bar();  // an 8 KB slice in a 16 KB slot
-  if (elect_one()) {
+  if (ROLE_ELECT()) {
     if (cx.rank == 0) mbar_expect_tx(fb, 2 * A_SLICE);
 #pragma unroll
     for (int q = 0; q < A_SPLIT; ++q)
       tma_load_2d_pair(dst + q * (A_SLICE / A_SPLIT), tm, 0, (int)(byte_off >> 8) + q * (A_SLICE / A_SPLIT / 256), fb);
   }
-  __syncwarp();
+  ROLE_SYNC();
   ra.advance();
 }
 // weight chunk (slice s, column block nb) of a GEMM group for this CTA
@@ -620,15 +643,23 @@ __device__ __forceinline__ void mma_step_b(Ctx& cx, Ring& rb, uint32_t a_addr, u
     cx.w[5] += clock64() - *(volatile long long*)ts_slot(0, rb.idx);  // load issue -> MMA-observed-full
 #endif
     tc_fence_after();
+#ifdef PNR_EXP_N64  // timing experiment: quarter-size MMAs (results are garbage)
+    const uint32_t idesc = idesc_bf16_f32(128, 64);
+#else
     const uint32_t idesc = idesc_bf16_f32(128, 256);
+#endif
     const uint32_t b_addr = cx.smem + OFF_BRING + rb.idx * B_CHUNK;
     const uint64_t da0 = smem_desc(a_addr, ROWS * 16, 128);
     const uint64_t db0 = smem_desc(b_addr, 128 * 16, 128);
     const uint32_t dcol = cx.tmem + d_col;
     const uint32_t ebar = rb.empty_bar();
-    if (elect_one()) {
+    if (ROLE_ELECT()) {
 #pragma unroll
+#ifdef PNR_EXP_ONE_MMA  // timing experiment: a quarter of the MMA instructions (results are garbage)
+      for (int kk = 0; kk < 1; ++kk) {
+#else
       for (int kk = 0; kk < 4; ++kk) {
+#endif
         // advancing K by 16 elements = 2 core-matrix panels: add to the (addr>>4) field only
         mma_bf16<2>(dcol, da0 + (uint64_t)(kk * 2 * (ROWS * 16) >> 4), db0 + (uint64_t)(kk * 2 * (128 * 16) >> 4), idesc,
                     (first && kk == 0) ? 0u : 1u);
@@ -638,13 +669,13 @@ __device__ __forceinline__ void mma_step_b(Ctx& cx, Ring& rb, uint32_t a_addr, u
       *(volatile long long*)ts_slot(1, rb.idx) = clock64();
 #endif
     }
-    __syncwarp();
+    ROLE_SYNC();
   }
   rb.advance();
 }
 __device__ __forceinline__ void signal(const Ctx& cx, int bar_idx) {
-  if (elect_one()) mma_commit<2>(cx.bar(bar_idx), 0x3);
-  __syncwarp();
+  if (ROLE_ELECT()) mma_commit<2>(cx.bar(bar_idx), 0x3);
+  ROLE_SYNC();
 }
 
 // x[:, all 512] (+)= A @ W^T over `nks` slices (k-outer) with A streamed through the ring: per slice the
@@ -656,8 +687,8 @@ __device__ __forceinline__ void gemm_from_ring(Ctx& cx, Ring& rb, int nks, uint3
     const uint32_t a_empty = rb.empty_bar();
     rb.advance();
     for (int nb = 0; nb < 2; ++nb) mma_step_b(cx, rb, a_addr, xcol + nb * 128, overwrite && s == 0);
-    if (elect_one()) mma_commit<2>(a_empty, 0x3);
-    __syncwarp();
+    if (ROLE_ELECT()) mma_commit<2>(a_empty, 0x3);
+    ROLE_SYNC();
   }
 }
 // NET = S_x @ W0^T, n-outer; waits for operand slices as the epilogue publishes them
@@ -879,6 +910,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
   const long long t_begin = clock64();
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + OFF_BARS + N_BARS * 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef PNR_EXP_NOLOAD
+  for (int i = threadIdx.x; i < NB_ST * B_CHUNK / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem_raw + OFF_BRING)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+#endif
   if (threadIdx.x == 0) setup_barriers(cx);
   if (warp == 2) {
     tmem_alloc<2>(smem_u32(tmem_slot), 512);
@@ -892,16 +927,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
   const int nsl = p.nks_z + p.nks_c;
 
   if (warp == 0) {
-    // ===================== producer (whole warp, uniform control flow) =====================
-    {
+    // ===================== producer =====================
+    if (ROLE_ENTER()) {
       Ring rb;
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), PNR_RING_A);
       uint32_t git = 0;
       for (int tile = pair; tile < p.tilesA; tile += npairs, ++git) {
         if (p.fused_gather) {  // this CTA's rows of the tile have been gathered (and are visible to TMA)
           twait(cx, 1, cx.bar(ZC_READY), git & 1, 203);
-          if (elect_one()) mbar_arrive(cx.bar(ZC_TAKEN));
-          __syncwarp();
+          if (ROLE_ELECT()) mbar_arrive(cx.bar(ZC_TAKEN));
+          ROLE_SYNC();
         }
         const size_t zt = ((size_t)(tile * 2 + cx.rank) * nsl) * A_SLICE;
         // (loops deliberately not unrolled: instruction footprint, see mbar_wait_slow)
@@ -931,8 +966,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer: leader CTA only, whole warp, uniform control flow ======
-    if (cx.rank == 0) {
+    // ===================== MMA issuer: leader CTA only ======
+    if (cx.rank == 0 && ROLE_ENTER()) {
       Ring rb;
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), PNR_RING_A);
       uint32_t use = 0;  // (tile-local block counter) parity source for SX/H barriers
@@ -1078,7 +1113,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
   // X (not the x3 load) separates two tiles on the tensor pipe.
 
   if (warp == 0) {
-    {
+    if (ROLE_ENTER()) {
       Ring rb;
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST_B);
       for (int tile = pair; tile < p.tilesB; tile += npairs)
@@ -1093,7 +1128,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
         }
     }
   } else if (warp == 1) {
-    if (cx.rank == 0) {
+    if (cx.rank == 0 && ROLE_ENTER()) {
       Ring rb;
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST_B);
       uint32_t use = 0, it = 0;
