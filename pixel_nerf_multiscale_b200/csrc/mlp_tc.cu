@@ -536,17 +536,29 @@ rows_to_operand_kernel(const float* __restrict__ zx, int d_latent, int d_in, int
 // the whole warp electing a lane around every instruction: the per-chunk control path (BRA.DIV / BSSY /
 // ELECT / R2UR) was the bound of both kernels -- with a quarter of the tensor work AND a quarter of the
 // weight traffic a tile still took 96 % of its cycles.
-#ifndef PNR_SOLO_ROLES
-#define PNR_SOLO_ROLES 1
+#ifndef PNR_SOLO_PROD
+#define PNR_SOLO_PROD 1
 #endif
-#if PNR_SOLO_ROLES
-#define ROLE_ELECT() true
-#define ROLE_SYNC() ((void)0)
-#define ROLE_ENTER() elect_one()
+#ifndef PNR_SOLO_MMA
+#define PNR_SOLO_MMA 1
+#endif
+#if PNR_SOLO_PROD
+#define PROD_ELECT() true
+#define PROD_SYNC() ((void)0)
+#define PROD_ENTER() elect_one()
 #else
-#define ROLE_ELECT() elect_one()
-#define ROLE_SYNC() __syncwarp()
-#define ROLE_ENTER() true
+#define PROD_ELECT() elect_one()
+#define PROD_SYNC() __syncwarp()
+#define PROD_ENTER() true
+#endif
+#if PNR_SOLO_MMA
+#define MMA_ELECT() true
+#define MMA_SYNC() ((void)0)
+#define MMA_ENTER() elect_one()
+#else
+#define MMA_ELECT() elect_one()
+#define MMA_SYNC() __syncwarp()
+#define MMA_ENTER() true
 #endif
 
 struct Ring {
@@ -596,7 +608,7 @@ __device__ __forceinline__ void load_b(Ctx& cx, Ring& rb, const CUtensorMap* tm,
 #endif
   const int row0 = (int)(byte_off >> 8);
   const uint32_t dst = cx.smem + OFF_BRING + rb.idx * B_CHUNK, fb = rb.full_bar();
-  if (ROLE_ELECT()) {  // operands computed in warp-uniform code -> uniform registers, no R2UR waterfall
+  if (PROD_ELECT()) {  // operands computed in warp-uniform code -> uniform registers, no R2UR waterfall
 #ifdef PNR_EXP_NOLOAD  // timing experiment: a quarter of the weight traffic (results are garbage)
     if (cx.rank == 0) mbar_expect_tx(fb, 2 * (B_CHUNK / 4));
     for (int q = 0; q < B_SPLIT / 4; ++q)
@@ -611,19 +623,19 @@ __device__ __forceinline__ void load_b(Ctx& cx, Ring& rb, const CUtensorMap* tm,
     *(volatile long long*)ts_slot(0, rb.idx) = clock64();
 #endif
   }
-  ROLE_SYNC();
+  PROD_SYNC();
   rb.advance();
 }
 __device__ __forceinline__ void load_a(Ctx& cx, Ring& ra, const CUtensorMap* tm, size_t byte_off) {
   twait(cx, 1, ra.empty_bar(), ra.phase ^ 1, 202);
   const uint32_t dst = cx.smem + OFF_BRING + ra.idx * B_CHUNK, fb = ra.full_bar();  // an 8 KB slice in a 16 KB slot
-  if (ROLE_ELECT()) {
+  if (PROD_ELECT()) {
     if (cx.rank == 0) mbar_expect_tx(fb, 2 * A_SLICE);
 #pragma unroll
     for (int q = 0; q < A_SPLIT; ++q)
       tma_load_2d_pair(dst + q * (A_SLICE / A_SPLIT), tm, 0, (int)(byte_off >> 8) + q * (A_SLICE / A_SPLIT / 256), fb);
   }
-  ROLE_SYNC();
+  PROD_SYNC();
   ra.advance();
 }
 // weight chunk (slice s, column block nb) of a GEMM group for this CTA
@@ -653,7 +665,7 @@ __device__ __forceinline__ void mma_step_b(Ctx& cx, Ring& rb, uint32_t a_addr, u
     const uint64_t db0 = smem_desc(b_addr, 128 * 16, 128);
     const uint32_t dcol = cx.tmem + d_col;
     const uint32_t ebar = rb.empty_bar();
-    if (ROLE_ELECT()) {
+    if (MMA_ELECT()) {
 #pragma unroll
 #ifdef PNR_EXP_ONE_MMA  // timing experiment: a quarter of the MMA instructions (results are garbage)
       for (int kk = 0; kk < 1; ++kk) {
@@ -669,13 +681,13 @@ __device__ __forceinline__ void mma_step_b(Ctx& cx, Ring& rb, uint32_t a_addr, u
       *(volatile long long*)ts_slot(1, rb.idx) = clock64();
 #endif
     }
-    ROLE_SYNC();
+    MMA_SYNC();
   }
   rb.advance();
 }
 __device__ __forceinline__ void signal(const Ctx& cx, int bar_idx) {
-  if (ROLE_ELECT()) mma_commit<2>(cx.bar(bar_idx), 0x3);
-  ROLE_SYNC();
+  if (MMA_ELECT()) mma_commit<2>(cx.bar(bar_idx), 0x3);
+  MMA_SYNC();
 }
 
 // x[:, all 512] (+)= A @ W^T over `nks` slices (k-outer) with A streamed through the ring: per slice the
@@ -687,8 +699,8 @@ __device__ __forceinline__ void gemm_from_ring(Ctx& cx, Ring& rb, int nks, uint3
     const uint32_t a_empty = rb.empty_bar();
     rb.advance();
     for (int nb = 0; nb < 2; ++nb) mma_step_b(cx, rb, a_addr, xcol + nb * 128, overwrite && s == 0);
-    if (ROLE_ELECT()) mma_commit<2>(a_empty, 0x3);
-    ROLE_SYNC();
+    if (MMA_ELECT()) mma_commit<2>(a_empty, 0x3);
+    MMA_SYNC();
   }
 }
 // NET = S_x @ W0^T, n-outer; waits for operand slices as the epilogue publishes them
@@ -928,15 +940,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
 
   if (warp == 0) {
     // ===================== producer =====================
-    if (ROLE_ENTER()) {
+    if (PROD_ENTER()) {
       Ring rb;
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), PNR_RING_A);
       uint32_t git = 0;
       for (int tile = pair; tile < p.tilesA; tile += npairs, ++git) {
         if (p.fused_gather) {  // this CTA's rows of the tile have been gathered (and are visible to TMA)
           twait(cx, 1, cx.bar(ZC_READY), git & 1, 203);
-          if (ROLE_ELECT()) mbar_arrive(cx.bar(ZC_TAKEN));
-          ROLE_SYNC();
+          if (PROD_ELECT()) mbar_arrive(cx.bar(ZC_TAKEN));
+          PROD_SYNC();
         }
         const size_t zt = ((size_t)(tile * 2 + cx.rank) * nsl) * A_SLICE;
         // (loops deliberately not unrolled: instruction footprint, see mbar_wait_slow)
@@ -967,7 +979,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: leader CTA only ======
-    if (cx.rank == 0 && ROLE_ENTER()) {
+    if (cx.rank == 0 && MMA_ENTER()) {
       Ring rb;
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), PNR_RING_A);
       uint32_t use = 0;  // (tile-local block counter) parity source for SX/H barriers
@@ -1113,7 +1125,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
   // X (not the x3 load) separates two tiles on the tensor pipe.
 
   if (warp == 0) {
-    if (ROLE_ENTER()) {
+    if (PROD_ENTER()) {
       Ring rb;
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST_B);
       for (int tile = pair; tile < p.tilesB; tile += npairs)
@@ -1128,7 +1140,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
         }
     }
   } else if (warp == 1) {
-    if (cx.rank == 0 && ROLE_ENTER()) {
+    if (cx.rank == 0 && MMA_ENTER()) {
       Ring rb;
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST_B);
       uint32_t use = 0, it = 0;
