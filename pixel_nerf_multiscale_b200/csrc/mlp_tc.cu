@@ -537,10 +537,7 @@ rows_to_operand_kernel(const float* __restrict__ zx, int d_latent, int d_in, int
 // ELECT / R2UR) was the bound of both kernels -- with a quarter of the tensor work AND a quarter of the
 // weight traffic a tile still took 96 % of its cycles.
 #ifndef PNR_SOLO_PROD
-#define PNR_SOLO_PROD 1
-#endif
-#ifndef PNR_SOLO_MMA
-#define PNR_SOLO_MMA 1
+#define PNR_SOLO_PROD 0  // the producer measured 0.3-0.9 % slower solo (A/B on C2 and C4)
 #endif
 #if PNR_SOLO_PROD
 #define PROD_ELECT() true
@@ -551,15 +548,12 @@ rows_to_operand_kernel(const float* __restrict__ zx, int d_latent, int d_in, int
 #define PROD_SYNC() __syncwarp()
 #define PROD_ENTER() true
 #endif
-#if PNR_SOLO_MMA
-#define MMA_ELECT() true
-#define MMA_SYNC() ((void)0)
-#define MMA_ENTER() elect_one()
-#else
-#define MMA_ELECT() elect_one()
-#define MMA_SYNC() __syncwarp()
-#define MMA_ENTER() true
-#endif
+// The issuer's mode is a template parameter (SM) of its helpers and of the phase-A kernel: solo is ~2 % faster
+// where the fc GEMMs dominate (L = 256: C2, C3) and ~4 % slower on the multi-scale L = 512 schema (C4),
+// measured A/B on one box; net_forward_tc picks by latent width.  Phase B always runs solo.
+template <bool SM> __device__ __forceinline__ bool mma_elect() { if constexpr (SM) return true; else return elect_one(); }
+template <bool SM> __device__ __forceinline__ void mma_sync() { if constexpr (!SM) __syncwarp(); }
+template <bool SM> __device__ __forceinline__ bool mma_enter() { if constexpr (SM) return elect_one(); else return true; }
 
 struct Ring {
   uint32_t full, empty;  // smem addresses of barrier arrays
@@ -648,6 +642,7 @@ __device__ __forceinline__ uint32_t wchunk(uint32_t off, int s, int nb, uint32_t
 // registers; only the tcgen05 / arrive instructions themselves are issued by one elected lane).
 // Only the leader CTA runs this role: waits until both CTAs' copies of the ring slot have landed
 // (both complete on its barrier), issues 4 MMAs (K=64) and releases the slot in both CTAs.
+template <bool SM>
 __device__ __forceinline__ void mma_step_b(Ctx& cx, Ring& rb, uint32_t a_addr, uint32_t d_col, bool first) {
   twait(cx, 0, rb.full_bar(), rb.phase, 301);
   if (cx.rank == 0) {
@@ -665,7 +660,7 @@ __device__ __forceinline__ void mma_step_b(Ctx& cx, Ring& rb, uint32_t a_addr, u
     const uint64_t db0 = smem_desc(b_addr, 128 * 16, 128);
     const uint32_t dcol = cx.tmem + d_col;
     const uint32_t ebar = rb.empty_bar();
-    if (MMA_ELECT()) {
+    if (mma_elect<SM>()) {
 #pragma unroll
 #ifdef PNR_EXP_ONE_MMA  // timing experiment: a quarter of the MMA instructions (results are garbage)
       for (int kk = 0; kk < 1; ++kk) {
@@ -681,49 +676,53 @@ __device__ __forceinline__ void mma_step_b(Ctx& cx, Ring& rb, uint32_t a_addr, u
       *(volatile long long*)ts_slot(1, rb.idx) = clock64();
 #endif
     }
-    MMA_SYNC();
+    mma_sync<SM>();
   }
   rb.advance();
 }
+template <bool SM>
 __device__ __forceinline__ void signal(const Ctx& cx, int bar_idx) {
-  if (MMA_ELECT()) mma_commit<2>(cx.bar(bar_idx), 0x3);
-  MMA_SYNC();
+  if (mma_elect<SM>()) mma_commit<2>(cx.bar(bar_idx), 0x3);
+  mma_sync<SM>();
 }
 
 // x[:, all 512] (+)= A @ W^T over `nks` slices (k-outer) with A streamed through the ring: per slice the
 // ring carries [A slice][W block 0][W block 1]; the A slot is released after both column blocks.
+template <bool SM>
 __device__ __forceinline__ void gemm_from_ring(Ctx& cx, Ring& rb, int nks, uint32_t xcol, bool overwrite) {
   for (int s = 0; s < nks; ++s) {
     twait(cx, 1, rb.full_bar(), rb.phase, 302);
     const uint32_t a_addr = cx.smem + OFF_BRING + rb.idx * B_CHUNK;
     const uint32_t a_empty = rb.empty_bar();
     rb.advance();
-    for (int nb = 0; nb < 2; ++nb) mma_step_b(cx, rb, a_addr, xcol + nb * 128, overwrite && s == 0);
-    if (MMA_ELECT()) mma_commit<2>(a_empty, 0x3);
-    MMA_SYNC();
+    for (int nb = 0; nb < 2; ++nb) mma_step_b<SM>(cx, rb, a_addr, xcol + nb * 128, overwrite && s == 0);
+    if (mma_elect<SM>()) mma_commit<2>(a_empty, 0x3);
+    mma_sync<SM>();
   }
 }
 // NET = S_x @ W0^T, n-outer; waits for operand slices as the epilogue publishes them
+template <bool SM>
 __device__ __forceinline__ void gemm_fc0(Ctx& cx, Ring& rb, uint32_t netcol, uint32_t sx_phase) {
   for (int nb = 0; nb < 2; ++nb) {
     for (int s = 0; s < DH / KS; ++s) {
       if (nb == 0 && cx.rank == 0) twait(cx, 2, cx.bar(SX_READY + s), sx_phase, 310 + s);
-      mma_step_b(cx, rb, cx.smem + OFF_SX + s * A_SLICE, netcol + nb * 128, s == 0);
+      mma_step_b<SM>(cx, rb, cx.smem + OFF_SX + s * A_SLICE, netcol + nb * 128, s == 0);
     }
-    signal(cx, NET_READY + nb);
+    signal<SM>(cx, NET_READY + nb);
   }
 }
 // X += H @ W1^T in four quarters (s 0-3 | nb 0,1), (s 4-7 | nb 0,1): the first half of X's columns
 // is final one quarter before the end, so its epilogue overlaps the last quarter, and the second
 // half of H is only needed from the third quarter on.  The producer streams chunks in this order.
+template <bool SM>
 __device__ __forceinline__ void gemm_fc1(Ctx& cx, Ring& rb, uint32_t xcol, uint32_t h_phase) {
   for (int sh = 0; sh < 2; ++sh)
     for (int nb = 0; nb < 2; ++nb) {
       for (int s = sh * 4; s < sh * 4 + 4; ++s) {
         if (nb == 0) twait(cx, 3, cx.bar(H_READY + s), h_phase, 320 + s);
-        mma_step_b(cx, rb, cx.smem + OFF_H + s * A_SLICE, xcol + nb * 128, false);
+        mma_step_b<SM>(cx, rb, cx.smem + OFF_H + s * A_SLICE, xcol + nb * 128, false);
       }
-      if (sh == 1) signal(cx, X_READY + nb);
+      if (sh == 1) signal<SM>(cx, X_READY + nb);
     }
 }
 
@@ -911,6 +910,7 @@ __device__ __noinline__ long long pool_tile(const Params& p, Ctx cx, const Epi e
 // =============================================================================================
 // Phase A
 // =============================================================================================
+template <bool SM>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phaseA_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Ctx cx;
@@ -979,24 +979,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: leader CTA only ======
-    if (cx.rank == 0 && MMA_ENTER()) {
+    if (cx.rank == 0 && mma_enter<SM>()) {
       Ring rb;
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), PNR_RING_A);
       uint32_t use = 0;  // (tile-local block counter) parity source for SX/H barriers
       uint32_t it = 0;
       for (int tile = pair; tile < p.tilesA; tile += npairs, ++it) {
         const uint32_t xcol = (it & 1) ? 256u : 0u, netcol = 256u - xcol;
-        gemm_from_ring(cx, rb, nsl, xcol, true);
+        gemm_from_ring<SM>(cx, rb, nsl, xcol, true);
         // The previous tile's pool must have consumed its X_READY completions before they are
         // signalled again (a waiter that misses one completion of a 1-count mbarrier waits for
         // ever), and it must have finished reading the old X before fc_0 reuses it as NET.
         if (it > 0) twait(cx, 4, cx.bar(XP_DONE), (it - 1) & 1, 330);
-        signal(cx, X_READY);
-        signal(cx, X_READY + 1);
+        signal<SM>(cx, X_READY);
+        signal<SM>(cx, X_READY + 1);
         for (int b = 0; b < p.n_pre; ++b, ++use) {
-          gemm_fc0(cx, rb, netcol, use & 1);
-          if (b + 1 < p.n_pre) gemm_from_ring(cx, rb, p.nks_z, xcol, false);
-          gemm_fc1(cx, rb, xcol, use & 1);
+          gemm_fc0<SM>(cx, rb, netcol, use & 1);
+          if (b + 1 < p.n_pre) gemm_from_ring<SM>(cx, rb, p.nks_z, xcol, false);
+          gemm_fc1<SM>(cx, rb, xcol, use & 1);
         }
       }
       if (p.stats && cx.rank == 0 && lane == 0) {
@@ -1140,7 +1140,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
         }
     }
   } else if (warp == 1) {
-    if (cx.rank == 0 && MMA_ENTER()) {
+    if (cx.rank == 0 && mma_enter<true>()) {
       Ring rb;
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST_B);
       uint32_t use = 0, it = 0;
@@ -1149,8 +1149,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
         // NET of this tile is the X of the previous one: its head epilogue must have read it
         if (it > 0 && p.n_post > 0) twait(cx, 4, cx.bar(XP_DONE), (it - 1) & 1, 530);
         for (int j = 0; j < p.n_post; ++j, ++use) {
-          gemm_fc0(cx, rb, netcol, use & 1);
-          gemm_fc1(cx, rb, xcol, use & 1);
+          gemm_fc0<true>(cx, rb, netcol, use & 1);
+          gemm_fc1<true>(cx, rb, xcol, use & 1);
         }
       }
     }
@@ -1427,7 +1427,10 @@ static int run_phases(const pnr_mlp& m, const Layout& L, const Plan& pl, int ns,
   PNR_TRY(encode_rows256(&p.tm_zc, pl.zc, (size_t)pl.tilesA * 2 * pl.nsl * A_SLICE, A_SLICE / A_SPLIT / 256));
   {
     ProfScope ps(PROF_PHASE_A, 2.0 * mac_pre * (double)P * ns, 0.0, st);
-    PNR_TRY(launch_cluster(mlp_phaseA_kernel, num_pairs(pl.tilesA), p, st));
+    // issuer mode by latent width (see mma_elect): PNR_SOLO_MMA=0/1 forces one of them
+    static const int force = [] { const char* e = getenv("PNR_SOLO_MMA"); return e ? atoi(e) : -1; }();
+    const bool solo = force >= 0 ? force != 0 : L.nks_z <= 4;
+    PNR_TRY(launch_cluster(solo ? mlp_phaseA_kernel<true> : mlp_phaseA_kernel<false>, num_pairs(pl.tilesA), p, st));
   }
   {
     ProfScope ps(PROF_PHASE_B, 2.0 * mac_post * (double)P, 0.0, st);
