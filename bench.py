@@ -231,6 +231,8 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one line (the JSON); NCCL's version / debug lines go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     net, renderer, conf, cam = build_scene(wl, device, args.precision)
     if world > 1:
