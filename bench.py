@@ -181,7 +181,16 @@ class ClockSampler:
                 "samples": len(sm), "power_w_median": pw[len(pw) // 2] if pw else None, "power_w_max": pw[-1] if pw else None}
 
 
+_json_out = sys.stdout
+
+
 def main():
+    # stdout carries exactly ONE line, the JSON: everything else any library writes to fd 1 (NCCL prints its
+    # version there on multi-GPU runs) is sent to stderr; the JSON goes to a duplicate of the original stdout
+    global _json_out
+    sys.stdout.flush()
+    _json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -220,7 +229,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": rate, "unit": unit, "cores": cores, "kind": "port", "sample": what},
-            "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), file=_json_out, flush=True)
         return
 
     # ------------------------------------------------------------------ our arm (GPU)
@@ -380,7 +389,7 @@ def main():
             "points_per_sec": value * 160, "clocks": clocks,
             "e2e": {"value": e2e, "unit": unit, "h2d_bytes_per_step": B * 8 * 4, "d2h_bytes_per_step": B * 4 * 4},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "torch_eager_gpu": eager}
-        print(json.dumps(line))
+        print(json.dumps(line), file=_json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
