@@ -329,14 +329,14 @@ def main():
             ach = pf[1] / (pms[1] * 1e-3) / 1e12
             traffic = None
             try:  # DRAM bytes of one launch of this kernel from the committed ncu --set full capture
-                prof = json.load(open(os.path.join(REPO, "profiles", "r01_v12_ncu_summary.json")))["mlp_phaseA_kernel"]
+                prof = json.load(open(os.path.join(REPO, "profiles", "r01_v13_ncu_summary.json")))["mlp_phaseA_kernel"]
                 scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
                 traffic = sum(float(prof[k][0]) * scale[prof[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
             except Exception:
                 pass
             roof = {"bound": "tensor", "kernel": "mlp_phaseA_kernel (fused gather + ResnetFC blocks 0..combine_layer-1 + view pool, tcgen05 cta_group::2)",
                     "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
-                    "traffic_note": "dram read+write bytes of ONE launch (~0.5 Mi points) from profiles/r01_v12_ncu_summary.json",
+                    "traffic_note": "dram read+write bytes of ONE launch (~0.5 Mi points) from profiles/r01_v13_ncu_summary.json",
                     "peak_source": peak_src, "launches": int(pl[1]), "avg_launch_ms": pms[1] / pl[1],
                     "share_of_step": pms[1] / ms,
                     "other_kernels": {

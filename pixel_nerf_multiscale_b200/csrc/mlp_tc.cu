@@ -102,6 +102,8 @@ struct Params {
   unsigned long long* stats;           // optional [pairs][16] cycle counters (debug)
   // in-kernel gather (warps 2-3 of phase A produce the operand image one tile ahead of the MMAs)
   int fused_gather;                    // 0: zc was written by point_features_bf16_kernel
+  int zc_ring;                         // > 0 (fused gather): zc holds zc_ring tiles per cluster pair, reused round-robin,
+                                       // so the image stays in L2 and is never written back to DRAM; 0: one slot per tile
   const float *xyz, *viewdirs, *rays, *zsamp;
   int K;
   pnr_scene sc;
@@ -950,7 +952,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
           if (PROD_ELECT()) mbar_arrive(cx.bar(ZC_TAKEN));
           PROD_SYNC();
         }
-        const size_t zt = ((size_t)(tile * 2 + cx.rank) * nsl) * A_SLICE;
+        const size_t zslot = p.zc_ring ? (size_t)pair * p.zc_ring + git % p.zc_ring : (size_t)tile;
+        const size_t zt = ((zslot * 2 + cx.rank) * nsl) * A_SLICE;
         // (loops deliberately not unrolled: instruction footprint, see mbar_wait_slow)
         for (int s = 0; s < nsl; ++s) {
           load_a(cx, rb, &p.tm_zc, zt + (size_t)s * A_SLICE);
@@ -1016,7 +1019,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
         bool valid;
         long long gp = tileA_point(tile, (int)cx.rank, row, p.ns, p.ppw, v, valid);
         valid = valid && gp < p.P;
-        uint8_t* base = const_cast<uint8_t*>(p.zc) + ((size_t)(tile * 2 + cx.rank) * nsl) * A_SLICE + (size_t)row * 16;
+        // slot (git % 3) of this pair: written while the producer still reads slot (git-1) % 3; slot git % 3 was
+        // last read for tile git-3, whose loads completed before the producer took tile git-1 (ZC_TAKEN)
+        const size_t zslot = p.zc_ring ? (size_t)pair * p.zc_ring + git % p.zc_ring : (size_t)tile;
+        uint8_t* base = const_cast<uint8_t*>(p.zc) + ((zslot * 2 + cx.rank) * nsl) * A_SLICE + (size_t)row * 16;
         gather_row_to_zc(p.sc, p.xyz, p.viewdirs, p.rays, p.zsamp, p.K, gp, v, valid, p.nks_z, p.nks_c, base);
         // generic-proxy global writes -> visible to the async proxy (TMA) of this SM before the signal
         __threadfence();
@@ -1413,6 +1419,8 @@ static int run_phases(const pnr_mlp& m, const Layout& L, const Plan& pl, int ns,
   p.apply_head = head;
   if (ga) {
     p.fused_gather = 1;
+    // the scratch holds one slot per tile: use it as a 3-deep ring per pair only when that needs fewer slots
+    p.zc_ring = (pl.tilesA > 3 * num_pairs(pl.tilesA)) ? 3 : 0;
     p.sc = *ga->sc;
     p.xyz = ga->xyz;
     p.viewdirs = ga->viewdirs;
