@@ -2,32 +2,47 @@
 """
 bench.py -- rays/s of the ray-rendering hot path (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c5] [--impl ours|reference]
 
-A "step" renders one ray batch (default 50 000 rays = the reference's --ray_batch_size,
-src/util/args.py:19) through render_par(rays) = NeRFRenderer.bind_parallel(net)(rays): 64 coarse +
-32 fine (16 importance + 16 depth) samples per ray, both MLPs.  Workloads (synthetic, seeded;
-SURVEY.md section 8d -- there is no dataset and no checkpoint):
-    c1  sn64  64x64   1 source view   conf/exp/sn64.conf  (single-scale, L=256)
-    c2  SRN   128x128 2 source views  conf/exp/srn.conf   (single-scale, L=256)     [default, N=1]
-    c3  DTU   300x400 3 source views  conf/exp/dtu.conf   (single-scale, L=256)
-    c4  DTU   300x400 3 source views  dtu.conf + encoder.use_multi_scale (pyramid, L=512)
+Default workload: c3, the DTU 3-view 300x400 render BASELINE.json quotes the metric on (configs[2]).
+A "step" renders ONE full-resolution frame of the camera orbit (120 000 rays for c3/c4) through the
+drivers' frame loop (eval/gen_video.py:174-237 = parallel.render_views): the frame's rays are sharded
+over the N ranks as contiguous ranges, every rank generates its own rays on its device,
+renders them in <= 50 000-ray batches (the reference's --ray_batch_size, src/util/args.py:19) through
+render_par(rays) = NeRFRenderer.bind_parallel(net)(rays) -- 64 coarse + 32 fine (16 importance + 16
+depth) samples per ray, both MLPs -- and ONE ncclAllGather of the packed (rgb, depth) rows brings the
+whole frame to every rank INSIDE the timed region.  Total work per step is fixed => "scaling": "strong".
+A weak-scaling leg (every rank renders its own 50 000-ray batches, no collective: what round 1
+reported) is measured next to it and printed under "weak".
+
+Workloads (synthetic, seeded; SURVEY.md section 8d -- there is no dataset and no checkpoint):
+    c1  sn64  64x64   1 source view   conf/exp/sn64.conf  (single-scale, L=256); step = 1 frame (4 096 rays)
+    c2  SRN   128x128 2 source views  conf/exp/srn.conf   (single-scale, L=256); step = one 50 000-ray
+        batch of the 40-frame gen_video orbit (batches cross frame borders, like torch.split in the driver)
+    c3  DTU   300x400 3 source views  conf/exp/dtu.conf   (single-scale, L=256); step = 1 frame    [default]
+    c4  DTU   300x400 3 source views  dtu.conf + encoder.use_multi_scale (pyramid, L=512); step = 1 frame
+    c5  eval.py sweep (eval/eval.py:199-292): 8 scenes x NS in {1,2,3} x V target views of 300x400; per
+        (scene, NS): encode (ResNet34, PyTorch) -> NHWC bf16 re-pack -> broadcast_scene over NCCL ->
+        sharded render of the V frames; everything inside the timed region; step = one (scene, NS) pair
 Source images are random, the ResNet34 encoder is random-init (eval mode; each feature level rescaled
 to unit RMS, as a trained encoder would emit), the two ResnetFC MLPs are re-randomised (at default
 init every block is the identity).
 
-Printed JSON (one line, rank 0): value = whole-job rays/s with rays resident in HBM; e2e = the same
-through the public API with rays in pinned host memory and rgb/depth read back every step;
-roofline = the dominant kernel (fused ResnetFC phase A) timed with CUDA events inside the timed
-region against the measured dense-bf16 peak; cpu_baseline = the oracle (a torch restatement of the
-reference's path, oracle/pixelnerf_oracle.py) on the host cores on a bounded ray sample.
---impl reference times that CPU path alone (the reference is Python and cannot travel to the
-GPU box; the oracle port is pinned against it by tests/golden).
+Printed JSON (one line, rank 0): value = whole-job rays/s with everything resident in HBM; e2e = the same
+frame loop fed from pinned HOST rays (each rank copies its slice H2D every step, like the reference's
+util.gen_rays(...).to(device)) with the gathered frame read back to pinned host memory every step;
+roofline = the dominant kernel (fused gather + ResnetFC) timed with CUDA events inside the timed
+region against the measured dense-bf16 peak; cpu_baseline = the UNMODIFIED reference renderer (staged
+under the git-ignored baseline/_ref by oracle/stage_reference.py; falls back to the oracle port when
+absent) on the host cores on a bounded ray sample; legs = the other configs, shorter runs of the same
+protocol.  --impl reference times that CPU path alone.
 """
 import argparse
+import ctypes
 import json
 import math
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -38,16 +53,33 @@ import torch
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
+DTU = dict(H=300, W=400, focal=(723.0, 723.0), c=(200.0, 150.0), z_near=0.1, z_far=5.0, radius=2.2)
 WORKLOADS = {
     "c1": dict(conf="conf/exp/sn64.conf", H=64, W=64, ns=1, focal=119.4, c=None, z_near=1.2, z_far=4.0, radius=2.6,
-               multi_scale=False, rays=4096, desc="sn64 64x64 NS=1 single-scale L=256"),
+               multi_scale=False, step="frame", video_frames=8, desc="sn64 64x64 NS=1 single-scale L=256"),
     "c2": dict(conf="conf/exp/srn.conf", H=128, W=128, ns=2, focal=131.25, c=None, z_near=0.8, z_far=1.8, radius=1.3,
-               multi_scale=False, rays=50000, desc="SRN car 128x128 NS=2 (views 64 104) single-scale L=256, 40-frame orbit"),
-    "c3": dict(conf="conf/exp/dtu.conf", H=300, W=400, ns=3, focal=(723.0, 723.0), c=(200.0, 150.0), z_near=0.1,
-               z_far=5.0, radius=2.2, multi_scale=False, rays=50000, desc="DTU 300x400 NS=3 (22 25 28) single-scale L=256"),
-    "c4": dict(conf="conf/exp/dtu.conf", H=300, W=400, ns=3, focal=(723.0, 723.0), c=(200.0, 150.0), z_near=0.1,
-               z_far=5.0, radius=2.2, multi_scale=True, rays=50000, desc="DTU 300x400 NS=3 multi-scale pyramid L=512"),
+               multi_scale=False, step="batch", video_frames=40,
+               desc="SRN car 128x128 NS=2 (views 64 104) single-scale L=256, 40-frame orbit"),
+    "c3": dict(conf="conf/exp/dtu.conf", ns=3, multi_scale=False, step="frame", video_frames=8,
+               desc="DTU 300x400 NS=3 (22 25 28) single-scale L=256", **DTU),
+    "c4": dict(conf="conf/exp/dtu.conf", ns=3, multi_scale=True, step="frame", video_frames=8,
+               desc="DTU 300x400 NS=3 multi-scale pyramid L=512", **DTU),
+    "c5": dict(conf="conf/exp/dtu.conf", ns=3, multi_scale=False, step="sweep", video_frames=1,
+               desc="eval.py sweep, 8 DTU-shaped scenes x NS 1/2/3, single-scale L=256", **DTU),
 }
+RAY_BATCH = 50000          # the reference's --ray_batch_size
+POINTS_PER_RAY = 160       # 64 coarse + 96 fine point evaluations
+
+
+def workload_config(name):
+    wl = WORKLOADS[name]
+    per = {"frame": "one full %dx%d frame (%d rays) per step" % (wl["W"], wl["H"], wl["W"] * wl["H"]),
+           "batch": "one %d-ray batch of the %d-frame orbit per step" % (RAY_BATCH, wl["video_frames"]),
+           "sweep": "one (scene, NS) pair per step: encode + re-pack + broadcast + V frames of %dx%d" % (wl["W"], wl["H"])}[wl["step"]]
+    return {"workload": "%s: %s; %s, rays sharded over the ranks, <= %d-ray batches, 64 coarse + 32 fine (16 depth) samples, "
+                        "2 MLPs (the CPU reference arm times a bounded ray sample of the same frames per step)"
+                        % (name, wl["desc"], per, RAY_BATCH),
+            "points_per_ray": POINTS_PER_RAY}
 
 
 def rerandomise(mlp, seed):
@@ -64,25 +96,30 @@ def rerandomise(mlp, seed):
         mlp.lin_out.bias[3] = 1.0
 
 
-def build_scene(wl, device, precision):
-    import pixel_nerf_multiscale_b200 as pk
+def load_conf(wl):
     from pixel_nerf_multiscale_b200.util.conf import ConfigFactory
 
     conf = ConfigFactory.parse_file(os.path.join(REPO, wl["conf"]))
     conf["model"]["encoder"].put("pretrained", False)
     conf["model"]["encoder"].put("use_multi_scale", bool(wl["multi_scale"]))
-    torch.manual_seed(0)
-    net = pk.make_model(conf["model"]).eval()
-    rerandomise(net.mlp_coarse, 1)
-    rerandomise(net.mlp_fine, 2)
-    net = net.to(device)
-    net.precision = precision
-    g = torch.Generator().manual_seed(7)
-    images = (torch.rand(1, wl["ns"], 3, wl["H"], wl["W"], generator=g) * 2 - 1).to(device)
-    poses = torch.stack([pk.util.pose_spherical(30.0 * i, -20.0, wl["radius"]) for i in range(wl["ns"])])[None].to(device)
+    return conf
+
+
+def source_views(wl, ns, device, seed=7):
+    """Synthetic source images / poses / intrinsics in the shapes the drivers pass to encode()."""
+    import pixel_nerf_multiscale_b200 as pk
+
+    g = torch.Generator().manual_seed(seed)
+    images = (torch.rand(1, ns, 3, wl["H"], wl["W"], generator=g) * 2 - 1).to(device)
+    poses = torch.stack([pk.util.pose_spherical(30.0 * i, -20.0, wl["radius"]) for i in range(ns)])[None].to(device)
     focal = torch.tensor(wl["focal"], dtype=torch.float32)
     focal = focal[None] if focal.dim() == 1 else focal
     c = None if wl["c"] is None else torch.tensor(wl["c"], dtype=torch.float32)[None]
+    return images, poses, focal, c
+
+
+def encode_scene(net, wl, ns, device, seed=7):
+    images, poses, focal, c = source_views(wl, ns, device, seed)
     with torch.no_grad():
         net.encode(images, poses, focal.to(device), c=None if c is None else c.to(device))
         # A random-init ResNet34 in eval mode has identity BatchNorm, so its activations grow ~10x per
@@ -91,22 +128,59 @@ def build_scene(wl, device, precision):
         for m in net.encoder.level_maps():
             m.div_(m.pow(2).mean().sqrt().clamp_min(1e-6))
         net.invalidate_scene()
-    renderer = pk.NeRFRenderer.from_conf(conf["renderer"], lindisp=False, eval_batch_size=wl["rays"])
-    return net, renderer, conf, dict(poses=poses, focal=focal, c=c)
+    return dict(poses=poses, focal=focal, c=c)
+
+
+def build_scene(wl, device, precision, ns=None, seed=7):
+    import pixel_nerf_multiscale_b200 as pk
+
+    conf = load_conf(wl)
+    torch.manual_seed(0)
+    net = pk.make_model(conf["model"]).eval()
+    rerandomise(net.mlp_coarse, 1)
+    rerandomise(net.mlp_fine, 2)
+    net = net.to(device)
+    net.precision = precision
+    cam = encode_scene(net, wl, wl["ns"] if ns is None else ns, device, seed)
+    renderer = pk.NeRFRenderer.from_conf(conf["renderer"], lindisp=False, eval_batch_size=RAY_BATCH)
+    return net, renderer, conf, cam
+
+
+def orbit_poses(wl, n_frames, device):
+    """Camera-to-world poses of a 360-degree orbit (eval/gen_video.py:157-172)."""
+    import pixel_nerf_multiscale_b200 as pk
+
+    angles = torch.linspace(-180, 180, n_frames + 1)[:-1]
+    return torch.stack([pk.util.pose_spherical(float(a), -10.0, wl["radius"]) for a in angles]).to(device)
 
 
 def orbit_rays(wl, cam, n_frames, device):
     """Rays of a 360-degree orbit (eval/gen_video.py:157-183 shape), flattened to (n, 8)."""
     import pixel_nerf_multiscale_b200 as pk
 
-    angles = torch.linspace(-180, 180, n_frames + 1)[:-1]
-    poses = torch.stack([pk.util.pose_spherical(float(a), -10.0, wl["radius"]) for a in angles]).to(device)
-    rays = pk.util.gen_rays(poses, wl["W"], wl["H"], cam["focal"], wl["z_near"], wl["z_far"], cam["c"])
+    rays = pk.util.gen_rays(orbit_poses(wl, n_frames, device), wl["W"], wl["H"], cam["focal"], wl["z_near"], wl["z_far"], cam["c"])
     return rays.reshape(-1, 8)
 
 
+def step_ranges(wl):
+    """[g0, g1) ray ranges of the steps over the flattened rays of the workload's video."""
+    per, total = wl["W"] * wl["H"], wl["video_frames"] * wl["W"] * wl["H"]
+    if wl["step"] == "batch":
+        return [(i, i + RAY_BATCH) for i in range(0, total - RAY_BATCH + 1, RAY_BATCH)]
+    return [(f * per, (f + 1) * per) for f in range(wl["video_frames"])]
+
+
+def renderer_kwargs(conf):
+    r = conf["renderer"]
+    return dict(n_coarse=r.get_int("n_coarse", 128), n_fine=r.get_int("n_fine", 0), n_fine_depth=r.get_int("n_fine_depth", 0),
+                depth_std=r.get_float("depth_std", 0.01), white_bkgd=bool(r.get_float("white_bkgd", False)), lindisp=False)
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arms: the staged reference itself (baseline/_ref) and the oracle port
+# ---------------------------------------------------------------------------------------------------
 def oracle_scene(net, cam, conf, device="cpu"):
-    """Oracle Scene sharing this net's weights / feature maps / cameras (CPU copies)."""
+    """Oracle Scene sharing this net's weights / feature maps / cameras (copies on `device`)."""
     from oracle import pixelnerf_oracle as po
     from oracle import synth
 
@@ -119,23 +193,76 @@ def oracle_scene(net, cam, conf, device="cpu"):
                     sd(net.mlp_fine), d_latent=net.latent_size, **hp)
 
 
-def cpu_render_rate(scene, conf, rays_cpu, steps, warmup):
-    """rays/s of the oracle port on the host cores (all threads)."""
+def reference_render_par(net, wl, cam, conf):
+    """render_par of the UNMODIFIED reference (CPU, fp32) holding this net's weights, feature maps and
+    cameras; None when the staged tree (baseline/_ref) is absent."""
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        return None
+    make_model, RefRenderer, _util = ref_loader.load()
+    rconf = load_conf(wl)
+    torch.manual_seed(0)
+    rnet = make_model(rconf["model"]).eval()
+    rnet.mlp_coarse.load_state_dict({k: v.detach().float().cpu() for k, v in net.mlp_coarse.state_dict().items()})
+    rnet.mlp_fine.load_state_dict({k: v.detach().float().cpu() for k, v in net.mlp_fine.state_dict().items()})
+    ns = net.num_views_per_obj
+    images, poses, focal, c = source_views(wl, ns, "cpu")
+    with torch.no_grad():
+        rnet.encode(images, poses, focal, c=c)
+    maps = [m.detach().float().cpu() for m in net.encoder.level_maps()]
+    rnet.encoder.latent = maps[-1]          # plain attributes in the fork (src/model/encoder.py:106-107)
+    rnet.encoder.latents = list(maps)
+    renderer = RefRenderer.from_conf(rconf["renderer"], lindisp=False, eval_batch_size=RAY_BATCH)
+    return renderer.bind_parallel(rnet, None, simple_output=True).eval()
+
+
+def cpu_arm(net, wl, cam, conf, rays_cpu, sample, steps, warmup, protocol=False):
+    """rays/s of the reference renderer (or, without the staged tree, the oracle port) on the host cores.
+    A step renders `sample` rays; with `protocol` additionally BASELINE.md section 3: a 256-ray warm-up and the
+    median of 3 calls on a 4 096-ray subsample; the oracle port is timed beside it on one step."""
     from oracle import pixelnerf_oracle as po
 
-    r = conf["renderer"]
-    kw = dict(n_coarse=r.get_int("n_coarse", 128), n_fine=r.get_int("n_fine", 0), n_fine_depth=r.get_int("n_fine_depth", 0),
-              depth_std=r.get_float("depth_std", 0.01), white_bkgd=bool(r.get_float("white_bkgd", False)), lindisp=False,
-              eval_batch_size=50000)
-    n = rays_cpu.shape[0]
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    ref = reference_render_par(net, wl, cam, conf)
+    kw = renderer_kwargs(conf)
+    scene = oracle_scene(net, cam, conf)
+    port = lambda r: po.render(scene, r[None], eval_batch_size=RAY_BATCH, **kw)
+    fn = (lambda r: ref(r[None])) if ref is not None else port
+    pick = torch.randperm(rays_cpu.shape[0], generator=torch.Generator().manual_seed(3))
+    batches = [rays_cpu[pick[i * sample:(i + 1) * sample]] for i in range(max(1, min(steps + warmup, rays_cpu.shape[0] // sample)))]
+    out = {}
     with torch.no_grad():
-        for _ in range(warmup):
-            po.render(scene, rays_cpu[None, : max(64, n // 8)], **kw)
+        torch.manual_seed(123)
+        fn(batches[0][:256])
+        for i in range(warmup):
+            fn(batches[i % len(batches)])
         t0 = time.perf_counter()
         for i in range(steps):
-            po.render(scene, rays_cpu[None], **kw)
+            fn(batches[(warmup + i) % len(batches)])
         dt = time.perf_counter() - t0
-    return steps * n / dt, dt / steps
+        out["value"], out["sec_per_step"] = steps * sample / dt, dt / steps
+        if ref is not None:
+            t0 = time.perf_counter()
+            port(batches[0])
+            out["port_value"] = sample / (time.perf_counter() - t0)
+        if protocol:
+            big = rays_cpu[pick[:4096]]
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                fn(big)
+                ts.append(time.perf_counter() - t0)
+            out["median_of_3_4096_rays"] = big.shape[0] / statistics.median(ts)
+    out.update(cores=cores, kind="reference" if ref is not None else "port", unit="rays/s",
+               sample="%d-ray sample of the workload's frames per step, %d timed steps after %d warm-up (+ one 256-ray call), fp32, "
+                      "torch %s CPU, %d threads; %s" % (
+                          sample, steps, warmup, torch.__version__, cores,
+                          "the UNMODIFIED reference (src/render/nerf.py + models.py.backup2 staged under baseline/_ref) through its "
+                          "own bind_parallel(...)(rays)" if ref is not None else
+                          "oracle port (oracle/pixelnerf_oracle.py): baseline/_ref is not staged on this box"))
+    return out
 
 
 class ClockSampler:
@@ -149,7 +276,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -181,6 +308,209 @@ class ClockSampler:
                 "samples": len(sm), "power_w_median": pw[len(pw) // 2] if pw else None, "power_w_max": pw[-1] if pw else None}
 
 
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+class Ctx:
+    def __init__(self, args):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            # stdout carries exactly one line (the JSON); NCCL's version / debug lines go to stderr
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+            dist.init_process_group("nccl", device_id=self.device)
+        from pixel_nerf_multiscale_b200 import _native as N
+
+        self.N, self.lib = N, N.lib()
+        self.precision = args.precision
+
+    def sync_all(self):
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            self.dist.barrier()
+            torch.cuda.synchronize(self.device)
+
+    def max_over_ranks(self, *vals):
+        if self.world == 1:
+            return vals
+        t = torch.tensor(vals, device=self.device, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return tuple(float(x) for x in t)
+
+    def sum_over_ranks(self, v):
+        if self.world == 1:
+            return v
+        t = torch.tensor([v], device=self.device, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t[0])
+
+    def tc_check(self):
+        self.N.check(self.lib.pnr_tc_check(self.N.stream_ptr(self.device)), "pnr_tc_check")
+
+
+def timed(cx, fn, steps, warmup, profile=False, sampler=None):
+    """W untimed + K timed calls of fn(i) between barrier + synchronize, CUDA events, max over ranks.
+    Returns (ms, launches over all ranks, profile arrays of rank 0 | None)."""
+    with torch.no_grad():
+        for i in range(warmup):
+            fn(i)
+        cx.tc_check()
+        cx.sync_all()
+        if sampler is not None:
+            sampler.start()
+        cx.lib.pnr_launch_count(1)
+        if profile:
+            cx.lib.pnr_profile_begin()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        ev1.record()
+        cx.sync_all()
+        ms = ev0.elapsed_time(ev1)
+        launches = int(cx.lib.pnr_launch_count(1))
+        prof = None
+        if profile:
+            pms, pl, pf, pb = (ctypes.c_double * 3)(), (ctypes.c_int64 * 3)(), (ctypes.c_double * 3)(), (ctypes.c_double * 3)()
+            cx.lib.pnr_profile_end(pms, pl, pf, pb)
+            prof = (list(pms), list(pl), list(pf), list(pb))
+        cx.tc_check()
+    (ms,) = cx.max_over_ranks(ms)
+    return ms, int(cx.sum_over_ranks(launches)), prof
+
+
+def measure(cx, wl_name, steps, warmup, profile=False, sampler=None, weak_steps=0):
+    """value / e2e (/ weak) of one workload.  Every rank calls this with the same arguments."""
+    from pixel_nerf_multiscale_b200.parallel import broadcast_scene, render_views
+
+    wl = WORKLOADS[wl_name]
+    dev = cx.device
+    net, renderer, conf, cam = build_scene(wl, dev, cx.precision)
+    if cx.world > 1:
+        # source-view state is produced once (rank 0) and broadcast over NVLink; no per-ray traffic
+        broadcast_scene(net, src=0)
+    render_par = renderer.bind_parallel(net, [cx.local_rank], simple_output=True).eval()
+    poses = orbit_poses(wl, wl["video_frames"], dev)
+    ranges = step_ranges(wl)
+    rays_step = ranges[0][1] - ranges[0][0]
+    geo = (wl["W"], wl["H"], cam["focal"], wl["z_near"], wl["z_far"])
+    torch.manual_seed(100 + cx.rank)
+
+    def step(i):
+        return render_views(render_par, poses, *geo, c=cam["c"], ray_batch_size=RAY_BATCH, ray_range=ranges[i % len(ranges)])
+
+    ms, launches, prof = timed(cx, step, steps, warmup, profile, sampler)
+    clocks = sampler.stop() if sampler is not None else None
+
+    # ---- end-to-end: rays from pinned host memory (each rank copies its slice), frame read back every step
+    host_rays = orbit_rays(wl, cam, wl["video_frames"], dev).cpu().pin_memory()
+    out_host = torch.empty(rays_step, 4).pin_memory()
+
+    def step_e2e(i):
+        rgb, depth = render_views(render_par, poses, *geo, c=cam["c"], ray_batch_size=RAY_BATCH,
+                                  ray_range=ranges[i % len(ranges)], host_rays=host_rays)
+        if cx.rank == 0:
+            out_host[:, :3].copy_(rgb, non_blocking=True)
+            out_host[:, 3].copy_(depth, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+
+    ms_e2e, _, _ = timed(cx, step_e2e, steps, min(warmup, 2))
+    res = {"ms": ms, "ms_e2e": ms_e2e, "launches": launches, "prof": prof, "clocks": clocks, "rays_per_step": rays_step,
+           "value": steps * rays_step / (ms * 1e-3), "e2e": steps * rays_step / (ms_e2e * 1e-3),
+           "net": net, "cam": cam, "conf": conf, "wl": wl}
+    if weak_steps > 0:
+        # weak-scaling leg (round 1's protocol): every rank renders its OWN 50 000-ray batches, no collective
+        all_rays = orbit_rays(wl, cam, wl["video_frames"], dev)
+        nb = max(1, all_rays.shape[0] // RAY_BATCH)
+        B = min(RAY_BATCH, all_rays.shape[0])
+        mine = [all_rays[((cx.rank + i * cx.world) % nb) * B:][:B].contiguous() for i in range(weak_steps + 3)]
+        ms_w, _, _ = timed(cx, lambda i: render_par(mine[i % len(mine)][None]), weak_steps, 3)
+        res["weak"] = {"value": cx.world * weak_steps * B / (ms_w * 1e-3), "unit": "rays/s", "scaling": "weak",
+                       "rays_per_gpu_per_step": B, "steps": weak_steps, "ms_per_step": ms_w / weak_steps,
+                       "note": "every rank renders its own %d-ray batches; no gather in the region" % B}
+    return res
+
+
+def measure_c5(cx, steps, warmup, views):
+    """eval.py sweep: per step one (scene, NS) pair -- rank 0 encodes, the state is broadcast, the V target
+    frames are rendered sharded and gathered.  encode / re-pack / broadcast are INSIDE the timed region."""
+    import pixel_nerf_multiscale_b200 as pk
+    from pixel_nerf_multiscale_b200.parallel import broadcast_scene, render_views
+
+    wl = WORKLOADS["c5"]
+    dev = cx.device
+    net, renderer, conf, cam = build_scene(wl, dev, cx.precision)
+    render_par = renderer.bind_parallel(net, [cx.local_rank], simple_output=True).eval()
+    pairs = [(s, ns) for s in range(8) for ns in (1, 2, 3)]
+    geo = (wl["W"], wl["H"], cam["focal"], wl["z_near"], wl["z_far"])
+    t_enc = []
+
+    def step(i):
+        s, ns = pairs[i % len(pairs)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if cx.rank == 0 or cx.world == 1:
+            encode_scene(net, wl, ns, dev, seed=1000 + s)
+        if cx.world > 1:
+            broadcast_scene(net, src=0)
+        net.native_scene()      # NCHW fp32 -> NHWC bf16 re-pack of the new feature maps
+        e1.record()
+        poses = torch.stack([pk.util.pose_spherical(-170.0 + 37.0 * (s * views + v), -10.0, wl["radius"]) for v in range(views)]).to(dev)
+        rgb, depth = render_views(render_par, poses, *geo, c=cam["c"], ray_batch_size=RAY_BATCH)
+        t_enc.append((e0, e1))
+        return rgb
+
+    ms, launches, _ = timed(cx, step, steps, warmup)
+    enc_ms = sum(a.elapsed_time(b) for a, b in t_enc[-steps:])
+    rays_step = views * wl["W"] * wl["H"]
+    return {"value": steps * rays_step / (ms * 1e-3), "unit": "rays/s", "steps": steps, "ms_per_step": ms / steps,
+            "rays_per_step": rays_step, "encode_pack_broadcast_ms_per_step": enc_ms / steps, "gpu_launches": launches,
+            "workload": workload_config("c5")["workload"],
+            "note": "%d target view(s) per (scene, NS) pair (eval.py renders up to 128; the share of encode/pack/broadcast "
+                    "shrinks with V); NS cycles 1,2,3 between steps" % views}
+
+
+def roofline(res, peaks):
+    prof = res["prof"]
+    if prof is None:
+        return None
+    pms, pl, pf, pb = prof
+    if pl[1] <= 0 or pms[1] <= 0:
+        return None
+    sus = peaks.get("bf16_tflops_sustained", 1400.0)
+    burst = peaks.get("bf16_tflops", 1650.0)
+    src = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained: the kernel is timed inside a long power-limited step; burst "
+           "figure beside it)") if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    ach = pf[1] / (pms[1] * 1e-3) / 1e12
+    traffic, tnote = None, None
+    for cand in ("r02_ncu_summary.json", "r01_v13_ncu_summary.json"):
+        try:  # DRAM bytes of one launch of this kernel from the committed ncu --set full capture
+            prof_j = json.load(open(os.path.join(REPO, "profiles", cand)))
+            k = next(v for n, v in prof_j.items() if n.startswith("mlp_phaseA") or n.startswith("mlp_fused"))
+            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+            traffic = sum(float(k[m][0]) * scale[k[m][1]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            tnote = "dram read+write bytes of ONE launch from profiles/" + cand
+            break
+        except Exception:
+            continue
+    total_f = pf[1] + pf[2]
+    total_ms = pms[1] + pms[2]
+    return {"bound": "tensor", "kernel": "fused gather + ResnetFC (tcgen05 cta_group::2): pre-pool blocks + view pool",
+            "achieved": ach, "peak": sus, "unit": "TFLOP/s", "frac": ach / sus, "peak_burst": burst, "frac_burst": ach / burst,
+            "traffic": traffic, "traffic_note": tnote, "peak_source": src, "launches": int(pl[1]),
+            "avg_launch_ms": pms[1] / pl[1], "share_of_step": pms[1] / res["ms"],
+            "mlp_total": {"TFLOPs": total_f / (total_ms * 1e-3) / 1e12 if total_ms > 0 else None,
+                          "share_of_step": total_ms / res["ms"], "frac": total_f / (total_ms * 1e-3) / 1e12 / sus if total_ms > 0 else None},
+            "other_kernels": {"mlp_phaseB_kernel": {"ms": pms[2], "launches": int(pl[2]),
+                                                    "TFLOPs": (pf[2] / (pms[2] * 1e-3) / 1e12) if pms[2] > 0 else None}}}
+
+
 _json_out = sys.stdout
 
 
@@ -199,122 +529,61 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the secondary workloads of the default run")
+    ap.add_argument("--c5-views", type=int, default=1)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    # same workload at every N so that the per-N values form one (weak) scaling series
-    wl_name = args.workload or "c2"
+    wl_name = args.workload or "c3"
     wl = WORKLOADS[wl_name]
     metric, unit = "rays/sec", "rays/s"
-    config = {"workload": "%s: %s; %d rays/step, 64 coarse + 32 fine (16 depth) samples, 2 MLPs" % (wl_name, wl["desc"], wl["rays"]),
-              "rays_per_step": wl["rays"], "points_per_ray": 160, "precision": args.precision}
+    config = workload_config(wl_name)
+    warmup = max(3, args.warmup)
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return
-        torch.set_num_threads(os.cpu_count() or 1)
         net, renderer, conf, cam = build_scene(wl, "cpu", "fp32")
-        scene = oracle_scene(net, cam, conf)
-        sample = 256
         rays = orbit_rays(wl, cam, 1, "cpu")
-        pick = torch.randperm(rays.shape[0], generator=torch.Generator().manual_seed(3))[:sample]
-        torch.manual_seed(123)
-        rate, sec = cpu_render_rate(scene, conf, rays[pick], max(1, args.steps), max(1, min(args.warmup, 1)))
-        cores = torch.get_num_threads()
-        what = "%d-ray sample of %s per step, torch %s CPU, %d threads" % (sample, wl_name, torch.__version__, cores)
+        sample = 1024
+        r = cpu_arm(net, wl, cam, conf, rays, sample, max(1, args.steps), max(1, args.warmup), protocol=True)
         print(json.dumps({
-            "impl": "reference", "metric": metric, "value": rate, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": rate, "unit": unit, "cores": cores, "kind": "port", "sample": what},
-            "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), file=_json_out, flush=True)
+            "impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "rays_per_step": sample,
+            "cpu_baseline": {k: r[k] for k in r if k != "sec_per_step"},
+            "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), file=_json_out, flush=True)
         return
 
     # ------------------------------------------------------------------ our arm (GPU)
-    import torch.distributed as dist
-
-    from pixel_nerf_multiscale_b200 import _native as N
-
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    if world > 1:
-        # stdout carries exactly one line (the JSON); NCCL's version / debug lines go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=device)
-    net, renderer, conf, cam = build_scene(wl, device, args.precision)
-    if world > 1:
-        # source-view state is produced once (rank 0) and broadcast over NVLink; no per-ray traffic
-        from pixel_nerf_multiscale_b200.parallel import broadcast_scene
-
-        broadcast_scene(net, src=0)
-    render_par = renderer.bind_parallel(net, [local_rank], simple_output=True).eval()
-    n_frames = 40 if wl_name == "c2" else (1 if wl_name == "c1" else 2)
-    all_rays = orbit_rays(wl, cam, n_frames, device)
-    B = wl["rays"]
-    n_batches = max(1, all_rays.shape[0] // B)
-    batches = [all_rays[i * B:(i + 1) * B].contiguous() for i in range(n_batches)]
-    # rank r renders its own slice of the batch list (rays are independent: no data-path collective)
-    mine = [batches[(rank + i * world) % n_batches] for i in range(args.steps + args.warmup)]
-    lib = N.lib()
-
-    def sync_all():
-        torch.cuda.synchronize(device)
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize(device)
-
-    torch.manual_seed(100 + rank)
-    with torch.no_grad():
-        for i in range(args.warmup):
-            render_par(mine[i][None])
-        N.check(lib.pnr_tc_check(N.stream_ptr(device)), "pnr_tc_check")
-        sync_all()
-        sampler = ClockSampler(local_rank)
+    cx = Ctx(args)
+    if wl_name == "c5":
+        r5 = measure_c5(cx, max(1, args.steps), warmup, args.c5_views)
         if rank == 0:
-            sampler.start()
-        lib.pnr_launch_count(1)
-        lib.pnr_profile_begin()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for i in range(args.steps):
-            rgb, depth = render_par(mine[args.warmup + i][None])
-        ev1.record()
-        sync_all()
-        ms = ev0.elapsed_time(ev1)
-        launches = int(lib.pnr_launch_count(1))
-        import ctypes as C
-
-        pms, pl, pf, pb = (C.c_double * 3)(), (C.c_int64 * 3)(), (C.c_double * 3)(), (C.c_double * 3)()
-        lib.pnr_profile_end(pms, pl, pf, pb)
-        clocks = sampler.stop() if rank == 0 else None
-        N.check(lib.pnr_tc_check(N.stream_ptr(device)), "pnr_tc_check")
-
-        # ---- end-to-end: rays from pinned host memory, rgb+depth read back every step
-        host_rays = [b.cpu().pin_memory() for b in mine[args.warmup:]]
-        out_rgb = torch.empty(1, B, 3).pin_memory()
-        out_d = torch.empty(1, B).pin_memory()
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(args.steps):
-            r = host_rays[i].to(device, non_blocking=True)
-            rgb, depth = render_par(r[None])
-            out_rgb.copy_(rgb, non_blocking=True)
-            out_d.copy_(depth, non_blocking=True)
-            torch.cuda.current_stream(device).synchronize()
-        e1.record()
-        sync_all()
-        ms_e2e = e0.elapsed_time(e1)
-
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
-    total_rays = world * args.steps * B
-    value = total_rays / (ms * 1e-3)
-    e2e = total_rays / (ms_e2e * 1e-3)
+            line = {"metric": metric, "value": r5["value"], "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+                    "ms_per_step": r5["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                    "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": config,
+                    "gpu_launches": r5["gpu_launches"], "c5": r5}
+            print(json.dumps(line), file=_json_out, flush=True)
+        if world > 1:
+            cx.dist.destroy_process_group()
+        return
+    sampler = ClockSampler(cx.local_rank) if rank == 0 else None
+    res = measure(cx, wl_name, args.steps, warmup, profile=True, sampler=sampler, weak_steps=max(5, args.steps // 2))
+    legs = {}
+    if args.workload is None and not args.no_legs:
+        k = max(3, args.steps // 2)
+        for other in ("c4", "c2", "c1"):
+            r = measure(cx, other, k, 3, profile=True)
+            roof = roofline(r, {}) if rank == 0 else None
+            legs[other] = {"value": r["value"], "unit": unit, "e2e": r["e2e"], "steps": k, "ms_per_step": r["ms"] / k,
+                           "rays_per_step": r["rays_per_step"], "workload": workload_config(other)["workload"],
+                           "fused_mlp_TFLOPs": roof["achieved"] if roof else None}
+            del r
+            torch.cuda.empty_cache()
+        r5 = measure_c5(cx, 6, 3, args.c5_views)
+        legs["c5"] = r5
 
     if rank == 0:
         peaks = {}
@@ -322,76 +591,51 @@ def main():
             peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-        peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
-        roof = None
-        if pl[1] > 0 and pms[1] > 0:
-            ach = pf[1] / (pms[1] * 1e-3) / 1e12
-            traffic = None
-            try:  # DRAM bytes of one launch of this kernel from the committed ncu --set full capture
-                prof = json.load(open(os.path.join(REPO, "profiles", "r01_v13_ncu_summary.json")))["mlp_phaseA_kernel"]
-                scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-                traffic = sum(float(prof[k][0]) * scale[prof[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-            except Exception:
-                pass
-            roof = {"bound": "tensor", "kernel": "mlp_phaseA_kernel (fused gather + ResnetFC blocks 0..combine_layer-1 + view pool, tcgen05 cta_group::2)",
-                    "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
-                    "traffic_note": "dram read+write bytes of ONE launch (~0.5 Mi points) from profiles/r01_v13_ncu_summary.json",
-                    "peak_source": peak_src, "launches": int(pl[1]), "avg_launch_ms": pms[1] / pl[1],
-                    "share_of_step": pms[1] / ms,
-                    "other_kernels": {
-                        "point_features_bf16_kernel": {"ms": pms[0], "launches": int(pl[0]),
-                                                       "algorithmic_GBps": (pb[0] / (pms[0] * 1e-3) / 1e9) if pms[0] > 0 else None},
-                        "mlp_phaseB_kernel": {"ms": pms[2], "launches": int(pl[2]),
-                                              "TFLOPs": (pf[2] / (pms[2] * 1e-3) / 1e12) if pms[2] > 0 else None}}}
-        cpu = None
-        if not args.no_cpu_baseline:
-            torch.set_num_threads(os.cpu_count() or 1)
-            scene = oracle_scene(net, cam, conf)
-            sample = 1024 if wl_name == "c1" else 512
-            pick = torch.randperm(all_rays.shape[0], generator=torch.Generator().manual_seed(3))[:sample]
-            torch.manual_seed(123)
-            rate, sec = cpu_render_rate(scene, conf, all_rays[pick.to(device)].cpu(), 2, 1)
-            cpu = {"value": rate, "unit": unit, "cores": torch.get_num_threads(), "kind": "port",
-                   "sample": "%d-ray sample of %s, 2 timed calls after 1 warm-up, oracle (torch %s CPU)" % (sample, wl_name, torch.__version__)}
-        eager = None
-        if not args.no_cpu_baseline:
+        net, cam, conf = res["net"], res["cam"], res["conf"]
+        cpu = eager = None
+        if not args.no_cpu_baseline and world == 1:
+            rays_cpu = orbit_rays(wl, cam, 1, cx.device).cpu()
+            r = cpu_arm(net, wl, cam, conf, rays_cpu, 1024, 4, 1)
+            cpu = {k: r[k] for k in r if k != "sec_per_step"}
             # honest software bar: the same oracle arithmetic as PyTorch eager ops on this
             # B200 (fp32, TF32 off), bounded sample; reported only, never the measured arm
             try:
                 from oracle import pixelnerf_oracle as po
 
                 torch.backends.cuda.matmul.allow_tf32 = False
-                gscene = oracle_scene(net, cam, conf, device=device)
+                gscene = oracle_scene(net, cam, conf, device=cx.device)
                 sample = 8192
-                rs = all_rays[torch.randperm(all_rays.shape[0], generator=torch.Generator().manual_seed(3))[:sample].to(device)]
-                r = conf["renderer"]
-                kw = dict(n_coarse=r.get_int("n_coarse", 128), n_fine=r.get_int("n_fine", 0),
-                          n_fine_depth=r.get_int("n_fine_depth", 0), depth_std=r.get_float("depth_std", 0.01),
-                          white_bkgd=bool(r.get_float("white_bkgd", False)), lindisp=False, eval_batch_size=200000)
+                all_rays = orbit_rays(wl, cam, 1, cx.device)
+                rs = all_rays[torch.randperm(all_rays.shape[0], generator=torch.Generator().manual_seed(3))[:sample].to(cx.device)]
+                kw = renderer_kwargs(conf)
                 with torch.no_grad():
-                    po.render(gscene, rs[None, :1024], **kw)
-                    torch.cuda.synchronize(device)
+                    po.render(gscene, rs[None, :1024], eval_batch_size=200000, **kw)
+                    torch.cuda.synchronize(cx.device)
                     t0 = time.perf_counter()
-                    po.render(gscene, rs[None], **kw)
-                    torch.cuda.synchronize(device)
+                    po.render(gscene, rs[None], eval_batch_size=200000, **kw)
+                    torch.cuda.synchronize(cx.device)
                     dt = time.perf_counter() - t0
                 eager = {"value": sample / dt, "unit": unit, "sample": "%d rays, oracle ops on cuda (torch %s eager, fp32)" % (sample, torch.__version__)}
                 del gscene
             except Exception as ex:  # pragma: no cover
                 eager = {"error": str(ex)[:200]}
+        R = res["rays_per_step"]
         line = {
-            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": dict(
-                config, l2="per-step working set (operand scratch + samples, >1 GB) far exceeds the 126 MB L2; "
-                           "consecutive steps render different ray batches"),
-            "points_per_sec": value * 160, "clocks": clocks,
-            "e2e": {"value": e2e, "unit": unit, "h2d_bytes_per_step": B * 8 * 4, "d2h_bytes_per_step": B * 4 * 4},
-            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "torch_eager_gpu": eager}
+            "metric": metric, "value": res["value"], "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": res["ms"] / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": config,
+            "rays_per_step": R, "points_per_sec": res["value"] * POINTS_PER_RAY,
+            "collective": ("ncclAllGather (torch.distributed all_gather_into_tensor) of the packed (rgb, depth) rows, %d B per step, "
+                           "inside the timed region; source-view state broadcast once before it" % (R * 16)) if world > 1 else
+                          "none at N=1 (same frame loop; the all-gather is skipped for a single rank)",
+            "l2": "per-step working set (operand scratch + samples, > 1 GB) far exceeds the 126 MB L2; consecutive steps render different frames",
+            "clocks": res["clocks"],
+            "e2e": {"value": res["e2e"], "unit": unit, "h2d_bytes_per_step": R * 8 * 4, "d2h_bytes_per_step": R * 4 * 4},
+            "gpu_launches": res["launches"], "roofline": roofline(res, peaks), "weak": res.get("weak"),
+            "cpu_baseline": cpu, "torch_eager_gpu": eager, "legs": legs or None}
         print(json.dumps(line), file=_json_out, flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        cx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -10,7 +10,11 @@
  *   - every function enqueues on the caller's stream and never synchronises the device;
  *   - every function returns 0 on success or a negative pnr_status; pnr_last_error() gives a
  *     thread-local message.  Nothing throws, nothing aborts;
- *   - no global mutable state: calls on different devices / streams / threads are independent.
+ *   - calls on different devices / streams / threads are independent.  Process-wide state is limited to
+ *     (a) one lazily created record PER DEVICE (SM count, "kernel attribute set" flags and the
+ *     barrier-fault word described at pnr_tc_check), guarded by a mutex, and (b) read-once
+ *     environment knobs (PNR_WAIT_TIMEOUT_MS, PNR_MAX_PAIRS, PNR_SOLO_MMA, PNR_CHUNK_ROWS_LOG2);
+ *     error message, launch counter, profile records and tensor-map cache are thread-local;
  *   - there is NO CPU implementation behind this ABI.
  */
 #ifndef PIXELNERF_B200_H
@@ -116,13 +120,18 @@ const char* pnr_last_error(void);
 int64_t pnr_launch_count(int reset);
 
 /* Synchronises `stream` and reports (then clears) a pipeline fault recorded by the tensor-core
- * kernels on the current device: their mbarrier waits are bounded, so a protocol error surfaces
- * here as PNR_ERR_CUDA instead of hanging the GPU.  Debug / test aid; never needed for results. */
+ * kernels on the CURRENT device: their mbarrier waits are wall-clock bounded (PNR_WAIT_TIMEOUT_MS,
+ * default 2000, 0 = unbounded for debuggers / sanitizers), so a protocol error surfaces as
+ * PNR_ERR_CUDA instead of hanging the GPU.  A fault is also reported, without synchronising, by
+ * the next pnr_net_forward / pnr_mlp_forward / pnr_render_rays call on that device. */
 int pnr_tc_check(pnr_stream stream);
+/* Debug: device buffer of [SM count / 2][16] uint64 per-role cycle counters written by the fused-MLP
+ * launches of the calling thread from now on (NULL = off; tools/tc_stats.py). */
+int pnr_tc_debug_stats(void* device_buffer);
 
 /* Optional per-kernel timing for the roofline report: between begin/end every tracked kernel is
  * bracketed by CUDA events on its launching stream.  Arrays have 3 entries:
- * [0] point-feature (gather) kernel, [1] MLP phase A (per point-view rows), [2] MLP phase B.
+ * [0] reserved (the gather runs inside [1]), [1] fused gather + ResnetFC kernel, [2] reserved.
  * flops/bytes are the ALGORITHMIC work of the tracked launches. */
 int pnr_profile_begin(void);
 int pnr_profile_end(double* ms, int64_t* launches, double* flops, double* bytes);

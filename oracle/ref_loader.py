@@ -8,8 +8,9 @@ oracle/pixelnerf_oracle.py can be pinned against it.  The reference's live
 functional model is ``src/model/models.py.backup2``, so ``model.models`` is
 loaded from that file, in place, without copying it.
 
-/root/reference exists only in the build container: nothing under ``-m gpu`` tests, smoke()
-or bench.py may call this module.
+/root/reference exists only in the build container.  On the GPU box the byte-identical staged copy under
+the git-ignored ``baseline/_ref`` (oracle/stage_reference.py) is used instead: that is what
+``bench.py --impl reference`` / ``cpu_baseline`` time and what the caller tests execute.
 """
 import importlib.machinery
 import importlib.util
@@ -17,12 +18,23 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("PIXELNERF_REFERENCE", "/root/reference")
 _HERE = os.path.dirname(os.path.abspath(__file__))
+_CANDIDATES = (os.environ.get("PIXELNERF_REFERENCE", "/root/reference"),
+               os.path.join(os.path.dirname(_HERE), "baseline", "_ref"))
+
+
+def _find_root():
+    for r in _CANDIDATES:
+        if os.path.isfile(os.path.join(r, "src", "model", "models.py.backup2")):
+            return r
+    return None
+
+
+REF_ROOT = _find_root() or _CANDIDATES[0]
 
 
 def available():
-    return os.path.isfile(os.path.join(REF_ROOT, "src", "model", "models.py.backup2"))
+    return _find_root() is not None
 
 
 def load():

@@ -67,6 +67,7 @@ EXPORTS = {
     "pnr_last_error": (C.c_char_p, []),
     "pnr_launch_count": (C.c_int64, [_i]),
     "pnr_tc_check": (_i, [_fp]),
+    "pnr_tc_debug_stats": (_i, [_fp]),
     "pnr_profile_begin": (_i, []),
     "pnr_profile_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "pnr_pack_level": (_i, [_fp, _i, _i, _i, _i, _fp, _i, _fp]),
@@ -89,6 +90,18 @@ EXPORTS = {
 }
 
 _lib = None
+_probe = None
+PROBE_LIB_PATH = os.path.join(_HERE, "libpixelnerf_b200_probe.so")
+
+
+def probe_lib():
+    """Hardware probes of the tcgen05 building blocks (csrc/tc_probe.cu): a separate library used by
+    tests/test_gpu_tc_probe.py and tools/probe_*.py only -- not part of the product ABI."""
+    global _probe
+    if _probe is None:
+        _probe = C.CDLL(PROBE_LIB_PATH)
+    return _probe
+
 
 
 def lib():

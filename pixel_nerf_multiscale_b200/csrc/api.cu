@@ -63,9 +63,11 @@ size_t mlp_tc_rows_workspace(const pnr_mlp& m, int SB, int NS, int P);
 int tc_check(cudaStream_t st);
 void tc_set_stats(unsigned long long* p);
 
-// pre-pool rows evaluated per internal chunk (bounds the scratch; rays are never split)
+// pre-pool rows evaluated per internal chunk (rays are never split).  fp32 validation path: bounds the
+// scratch.  bf16 path: the fused kernel keeps all intermediates on chip / in two small L2-resident rings, so
+// a whole pass is ONE launch; the cap only keeps 32-bit point indices valid.
 static const long long kChunkRowsF32 = 1LL << 18;
-static const long long kChunkRowsBF16 = 1LL << 20;
+static const long long kChunkRowsBF16 = 1LL << 30;
 
 static int validate_scene(const pnr_scene* sc) {
   PNR_CHECK_ARG(sc != nullptr, "scene is NULL");
@@ -121,7 +123,7 @@ static long long bf16_chunk_rows() {
   static long long rows = [] {  // PNR_CHUNK_ROWS_LOG2: experiment knob (scratch grows with it)
     const char* e = getenv("PNR_CHUNK_ROWS_LOG2");
     int l = e ? atoi(e) : 0;
-    return (l >= 14 && l <= 26) ? (1LL << l) : kChunkRowsBF16;
+    return (l >= 14 && l <= 30) ? (1LL << l) : kChunkRowsBF16;
   }();
   return rows;
 }
@@ -224,7 +226,8 @@ int pnr_profile_end(double* ms, int64_t* launches, double* flops, double* bytes)
   return PNR_OK;
 }
 
-// debug: device buffer of [74][16] cycle counters filled by the LAST phase-A launch (NULL = off)
+// debug: device buffer of [SMs/2][16] uint64 cycle counters filled by the next fused-MLP launches of this
+// thread (NULL = off)
 int pnr_tc_debug_stats(void* device_buffer) {
   tc_set_stats((unsigned long long*)device_buffer);
   return PNR_OK;
@@ -236,7 +239,8 @@ int pnr_pack_level(const float* src, int n_views, int C, int H, int W, void* dst
   PNR_CHECK_ARG(src && dst, "pack_level: NULL pointer");
   PNR_CHECK_ARG(n_views > 0 && C > 0 && H > 0 && W > 0, "pack_level: bad shape");
   PNR_CHECK_ARG(dst_dtype == PNR_FP32 || dst_dtype == PNR_BF16, "pack_level: bad dtype");
-  PNR_CHECK_ARG((long long)n_views * H < 65536LL * 32768LL, "pack_level: too many rows");
+  PNR_CHECK_ARG((long long)n_views * H <= 65535LL, "pack_level: n_views * H = %lld exceeds 65535 (grid z limit)",
+                (long long)n_views * H);
   return launch_pack_level(src, n_views, C, H, W, dst, dst_dtype, (cudaStream_t)stream);
 }
 
@@ -268,6 +272,7 @@ int pnr_net_forward(const pnr_scene* scene, const pnr_mlp* mlp, const float* xyz
   PNR_TRY(validate_scene(scene));
   PNR_TRY(validate_mlp(mlp, scene, precision));
   PNR_CHECK_ARG(xyz && out, "net_forward: NULL pointer");
+  PNR_CHECK_ARG(((uintptr_t)out & 15) == 0, "net_forward: out must be 16-byte aligned");
   PNR_CHECK_ARG(!scene->use_viewdirs || viewdirs, "net_forward: viewdirs required (use_viewdirs)");
   PNR_CHECK_ARG(SB * scene->ns == scene->n_views, "net_forward: SB*NS != n_views");
   if (SB == 0 || P == 0) return PNR_OK;
@@ -279,6 +284,7 @@ int pnr_mlp_forward(const pnr_mlp* mlp, const float* zx, int SB, int NS, int P, 
                     void* workspace, size_t workspace_bytes, pnr_stream stream) {
   PNR_TRY(validate_mlp(mlp, nullptr, precision));
   PNR_CHECK_ARG(zx && out, "mlp_forward: NULL pointer");
+  PNR_CHECK_ARG(((uintptr_t)out & 15) == 0, "mlp_forward: out must be 16-byte aligned");
   PNR_UNSUPPORTED(NS > 1 && mlp->combine_layer >= mlp->n_blocks, "multi-view rows need combine_layer < n_blocks");
   if (precision == PNR_FP32)
     return mlp_forward_f32(*mlp, zx, SB, NS, P, out, false, workspace, workspace_bytes, (cudaStream_t)stream);

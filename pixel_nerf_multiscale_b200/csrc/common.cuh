@@ -59,7 +59,8 @@ int64_t& launch_counter();
 
 // optional per-kernel timing (bench.py's roofline leg): CUDA events recorded on the launching
 // stream around the tracked kernels; thread-local, off by default.
-enum ProfKind { PROF_FEATURES = 0, PROF_PHASE_A = 1, PROF_PHASE_B = 2, PROF_KINDS = 3 };
+enum ProfKind { PROF_FEATURES = 0, PROF_FUSED_MLP = 1, PROF_RESERVED = 2, PROF_KINDS = 3 };
+#define PNR_MAX_DEVICES 64
 struct ProfScope {
   int kind;
   cudaStream_t st;

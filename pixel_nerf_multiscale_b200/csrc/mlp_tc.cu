@@ -1,9 +1,10 @@
 // Kernels (a)+(b), production path: fused point-feature gather + ResnetFC
 // (src/model/models.py.backup2:155-282, src/model/resnetfc.py:173-236) as a chain of tcgen05
-// (UTCHMMA.2CTA) GEMMs with bf16 operands and fp32 accumulation in tensor memory.
+// (UTCHMMA.2CTA) GEMMs with bf16 operands and fp32 accumulation in tensor memory -- ONE persistent
+// kernel per network evaluation (mlp_fused_kernel).
 //
-// Design ("pair-64"): a cluster of 2 CTAs owns a tile of 128 (point,view) rows, 64 rows per CTA, and
-// issues cta_group::2 MMAs with M=128, N=256, K=16.  Per CTA:
+// Design ("pair-64"): a cluster of 2 CTAs owns a tile of 128 rows, 64 rows per CTA, and issues
+// cta_group::2 MMAs with M=128, N=256, K=16.  Per CTA:
 //   TMEM  512 columns = X (64 rows x 512 fp32 residual stream, accumulated IN PLACE by the lin_z and
 //         fc_1 GEMMs, so the residual add costs nothing and never leaves fp32) + NET (fc_0 output)
 //   smem  S_x = relu(x) bf16 (64 KB) and H = relu(net) bf16 (64 KB) as K-major SWIZZLE_NONE UMMA
@@ -15,15 +16,20 @@
 //         warp 2 also owns the TMEM allocation) | 4-11 epilogue (TMEM -> +bias, relu -> bf16 operand
 //         panels; view mean-pool; lin_out head).  Producer and issuer run warp-uniform, electing one
 //         lane only around the instruction, so descriptors live in uniform registers.
-// Phase A (rows = points x views): gather, lin_in+lin_z[0], blocks 0..combine_layer-1 with the next
-//         block's lin_z GEMM scheduled between fc_0 and fc_1, view mean-pool
-//         (util.combine_interleaved) -> pooled x (fp32) to global.
-// Phase B (rows = points): remaining blocks, lin_out, sigmoid/relu head (models.py.backup2:274-281).
+// A pair walks its tiles in GROUPS: nA = 64 / (64 / NS) "A tiles" (rows = points x views: gather,
+//         lin_in+lin_z[0], blocks 0..combine_layer-1 with the next block's lin_z GEMM scheduled between
+//         fc_0 and fc_1, view mean-pool = util.combine_interleaved), whose pooled fp32 rows (64/NS points
+//         per CTA and tile) are parked in a 128 KB per-CTA staging buffer that is rewritten every group
+//         and therefore stays in L2, followed by one "B tile" (rows = the group's pooled points, 64 per
+//         CTA): remaining blocks, lin_out on CUDA cores from TMEM, sigmoid/relu head
+//         (models.py.backup2:274-281).  Nothing but rays/samples in and (rgb, sigma) out touches DRAM.
 // Every mbarrier wait is wall-clock bounded; a protocol fault writes its tag to pinned host memory
-// and traps (pnr_tc_check reports it) instead of hanging the GPU.
+// and traps (the next call on that device reports it) instead of hanging the GPU.
 #include <cstdlib>
 #include <cuda.h>
 #include <stdlib.h>
+
+#include <mutex>
 
 #include "features.cuh"
 #include "tc_ptx.cuh"
@@ -31,18 +37,6 @@
 namespace pnr {
 using namespace ptx;
 
-// first barrier-timeout tag seen by any tensor-core kernel on this device (0 = none); read and
-// cleared by pnr_tc_check().  A protocol bug therefore fails loudly instead of hanging the GPU.
-// The word lives in mapped pinned host memory so that it can be read even after the kernel trapped.
-static int* g_err_host = nullptr;   // host view
-static int* g_err_dev = nullptr;    // device view of the same word
-static int ensure_err_word() {
-  if (g_err_host) return PNR_OK;
-  PNR_CUDA(cudaHostAlloc((void**)&g_err_host, 64, cudaHostAllocMapped | cudaHostAllocPortable));
-  g_err_host[0] = 0;
-  PNR_CUDA(cudaHostGetDevicePointer((void**)&g_err_dev, g_err_host, 0));
-  return PNR_OK;
-}
 static thread_local unsigned long long* g_stats_ptr = nullptr;  // debug cycle counters (host pointer holder)
 void tc_set_stats(unsigned long long* p) { g_stats_ptr = p; }
 
@@ -60,7 +54,6 @@ constexpr int NB_ST = 6;                // unified operand ring: weight chunks (
 #ifndef PNR_RING_A
 #define PNR_RING_A NB_ST                // experiment knob: ring slots phase A actually uses (<= NB_ST); 4/5/6 -> 632k/654k/665k rays/s on C2
 #endif
-constexpr int NB_ST_B = 5;              // phase B: 5 slots, the 6th holds the lin_out weights / partial sums
 #ifndef PNR_B_SPLIT
 #define PNR_B_SPLIT 2
 #endif
@@ -72,7 +65,6 @@ constexpr int A_SPLIT = PNR_A_SPLIT;    // TMA boxes per operand slice
 constexpr int OFF_SX = 0;
 constexpr int OFF_H = OFF_SX + ROWS * DH * 2;
 constexpr int OFF_BRING = OFF_H + ROWS * DH * 2;
-constexpr int OFF_LINOUT = OFF_BRING + NB_ST_B * B_CHUNK;
 constexpr int OFF_BARS = OFF_BRING + NB_ST * B_CHUNK;
 constexpr int SMEM_BYTES = OFF_BARS + 512;
 constexpr int THREADS = 384;
@@ -92,16 +84,17 @@ struct Params {
   int n_pre, n_post;                   // blocks before / after the view pool
   int nks_z, nks_c;                    // K slices of the latent / code part of an input row
   int ns, ppw;                         // views per point, points per CTA (= 64 / ns; rows pl*ns + v)
+  int nA;                              // A tiles per group (= 64 / ppw): their pooled points fill one B tile
   long long P;                         // points
-  int tilesA, tilesB;
+  int tilesA;
   const uint8_t* zc;                   // [tileA][cta][slice][A_SLICE]
-  float* x3;                           // pooled residual stream, phase-B tile order
+  float* stage;                        // pooled residual rows of the current group: [CTA][nb][h][col/4][row (64)][4] fp32
   float* out;                          // (P,4)
   int apply_head;
   int* err;
   unsigned long long* stats;           // optional [pairs][16] cycle counters (debug)
   // in-kernel gather (warps 2-3 of phase A produce the operand image one tile ahead of the MMAs)
-  int fused_gather;                    // 0: zc was written by point_features_bf16_kernel
+  int fused_gather;                    // 0: zc was written by rows_to_operand_kernel (pnr_mlp_forward)
   int zc_ring;                         // > 0 (fused gather): zc holds zc_ring tiles per cluster pair, reused round-robin,
                                        // so the image stays in L2 and is never written back to DRAM; 0: one slot per tile
   const float *xyz, *viewdirs, *rays, *zsamp;
@@ -261,8 +254,8 @@ int mlp_tc_pack(const pnr_mlp& m, void* dst, size_t dst_bytes, cudaStream_t st) 
 }
 
 // =============================================================================================
-// kernel (a), bf16 operand variant: one warp per tile row; writes [latent | code] straight into the
-// phase-A operand image  zc[tile][cta][k-group][row][8 bf16]
+// kernel (a), bf16 operand variant (gather warps of the fused kernel): [latent | code] straight into the
+// A-tile operand image  zc[slot][cta][k-group][row][8 bf16]
 // =============================================================================================
 __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -331,92 +324,6 @@ __device__ __forceinline__ Taps make_taps_fast(float u, float v, int H, int W, f
   t.w10 = yin ? fx0 * fy1 : 0.f;
   t.w11 = (xin && yin) ? fx1 * fy1 : 0.f;
   return t;
-}
-
-__global__ void __launch_bounds__(256)
-point_features_bf16_kernel(const pnr_scene sc, const float* __restrict__ xyz, const float* __restrict__ viewdirs,
-                           const float* __restrict__ rays, const float* __restrict__ z, int K, long long P, int ppw,
-                           int tilesA, int nks_z, int nks_c, uint8_t* __restrict__ zc) {
-  const int lane = threadIdx.x & 31;
-  const long long wrow = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (wrow >= (long long)tilesA * 128) return;
-  const int tile = (int)(wrow >> 7), cta = (int)((wrow >> 6) & 1), row = (int)(wrow & 63);
-  int v;
-  bool valid;
-  long long gp = tileA_point(tile, cta, row, sc.ns, ppw, v, valid);
-  valid = valid && gp < P;
-  const int nsl = nks_z + nks_c;
-  uint8_t* base = zc + ((size_t)(tile * 2 + cta) * nsl) * A_SLICE + (size_t)row * 16;  // + kgroup*1024
-  if (!valid) {
-    for (int g = lane; g < nsl * 8; g += 32) *reinterpret_cast<uint4*>(base + (size_t)g * 1024) = make_uint4(0, 0, 0, 0);
-    return;
-  }
-  float X[3], D[3];
-  if (rays != nullptr) {
-    const unsigned gpu = (unsigned)gp, r = gpu / (unsigned)K;  // a chunk never exceeds 2^31 points
-    const float4 ra = __ldg(reinterpret_cast<const float4*>(rays) + 2 * (size_t)r);
-    const float4 rb = __ldg(reinterpret_cast<const float4*>(rays) + 2 * (size_t)r + 1);
-    const float t = __ldg(z + gpu);
-    X[0] = ra.x + t * ra.w;  // o + z * d
-    X[1] = ra.y + t * rb.x;
-    X[2] = ra.z + t * rb.y;
-    D[0] = ra.w;
-    D[1] = rb.x;
-    D[2] = rb.y;
-  } else {
-    load_point(xyz, viewdirs, nullptr, nullptr, 0, gp, X, D);
-  }
-  PointCam pc;
-  camera_project(sc.cams + v * 16, X, D, pc);
-  // ---- latent: lanes stride over all 8-channel groups of all levels ----
-  const int G = sc.d_latent >> 3;
-  for (int g = lane; g < G; g += 32) {
-    int l = 0;
-    while (l + 1 < sc.n_levels && (g << 3) >= sc.ch_off[l + 1]) ++l;
-    const int C = sc.C[l], H = sc.H[l], W = sc.W[l];
-    const Taps t = make_taps_fast(pc.u, pc.v, H, W, sc.kx[l], sc.ky[l]);
-    const int C8 = C >> 3, gl = g - (sc.ch_off[l] >> 3);
-    const uint4* f = reinterpret_cast<const uint4*>(sc.level[l]) + (size_t)v * H * W * C8 + gl;
-    // 4 x 128-bit loads: 8 consecutive channels of each tap (NHWC: a warp reads 512 contiguous B per tap)
-    const uint4 q00 = __ldg(f + (size_t)t.o00 * C8), q01 = __ldg(f + (size_t)t.o01 * C8);
-    const uint4 q10 = __ldg(f + (size_t)t.o10 * C8), q11 = __ldg(f + (size_t)t.o11 * C8);
-    float a[8], b[8], c[8], d[8];
-    bf16x8_to_float(q00, a);
-    bf16x8_to_float(q01, b);
-    bf16x8_to_float(q10, c);
-    bf16x8_to_float(q11, d);
-    uint32_t o[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float lo = a[2 * e] * t.w00 + b[2 * e] * t.w01 + c[2 * e] * t.w10 + d[2 * e] * t.w11;
-      float hi = a[2 * e + 1] * t.w00 + b[2 * e + 1] * t.w01 + c[2 * e + 1] * t.w10 + d[2 * e + 1] * t.w11;
-      o[e] = pack_bf16x2(lo, hi);
-    }
-    *reinterpret_cast<uint4*>(base + (size_t)g * 1024) = make_uint4(o[0], o[1], o[2], o[3]);
-  }
-  // ---- positional code: every lane evaluates entries lane, lane+32, ...; groups of 8 consecutive
-  //      entries are then collected into one lane by shuffles and stored as one 16-byte k-group ----
-  CodeCtx cc;
-  cc.dz = sc.use_xyz ? 3 : 1;
-  cc.db = cc.dz + ((sc.use_viewdirs && sc.use_code && sc.use_code_viewdirs) ? 3 : 0);
-  cc.coded = sc.use_code ? (sc.num_freqs * 2 * cc.db + (sc.include_input ? cc.db : 0)) : cc.db;
-  cc.d_in = sc.d_in;
-  cc.use_code = sc.use_code;
-  cc.include_input = sc.include_input;
-  cc.use_xyz = sc.use_xyz;
-  cc.normalize_z = sc.normalize_z;
-  cc.freq_factor = sc.freq_factor;
-  for (int t = 0; t < nks_c * 2; ++t) {  // 32 entries per pass -> 4 groups
-    const float e = code_entry_fast(cc, pc, t * 32 + lane);
-    float w[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) w[k] = __shfl_sync(0xffffffffu, e, ((lane & 3) << 3) + k);
-    if (lane < 4) {
-      const int g = t * 4 + lane;
-      *reinterpret_cast<uint4*>(base + (size_t)(nks_z * 8 + g) * 1024) =
-          make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]), pack_bf16x2(w[4], w[5]), pack_bf16x2(w[6], w[7]));
-    }
-  }
 }
 
 // Per-lane variant used by the gather warps inside phase A: lane = one row of the tile; the lane loops
@@ -804,14 +711,15 @@ __device__ __forceinline__ void setup_barriers(const Ctx& cx) {
   fence_mbar_init();
 }
 
-// View mean-pool of one tile's residual stream (TMEM X) -> pooled x (fp32) in phase-B tile order.
+// View mean-pool of one A tile's residual stream (TMEM X) -> pooled x (fp32) rows krow0.. of this CTA's
+// staging buffer (the group's B tile reads them back).
 // Runs once per tile, i.e. with cold instruction cache lines every time (the kernel is far larger
 // than the I-cache and the other roles keep running): one compact out-of-line body per view count,
 // selected once, instead of code specialised on p.ns inline (which spread the executed path over
 // ~100 KB of SASS and cost ~10K cycles per tile in instruction fetch alone).  NS = 0: any view count.
 template <int NS>
-__device__ __noinline__ long long pool_tile(const Params& p, Ctx cx, const Epi e, int tile, uint32_t xcol, uint32_t xph,
-                                            uint32_t it, uint8_t* smem_raw) {
+__device__ __noinline__ long long pool_tile(const Params& p, Ctx cx, const Epi e, int tile, int krow0, uint32_t xcol,
+                                            uint32_t xph, uint32_t it, uint8_t* smem_raw) {
   const int ns = NS ? NS : p.ns;
   const int lane = e.lane;
   const float* biasA = reinterpret_cast<const float*>(p.w + p.off_biasA);
@@ -821,8 +729,8 @@ __device__ __noinline__ long long pool_tile(const Params& p, Ctx cx, const Epi e
   valid = valid && v == 0 && gp < p.P;
   const float* bP = biasA + (size_t)p.n_pre * DH;
   const float inv = 1.0f / (float)ns;
-  const long long tb = gp >> 7;
-  const int cb = (int)((gp >> 6) & 1), rb_ = (int)(gp & 63);
+  const int rb_ = krow0 + e.row / ns;  // staging row of this lane's point
+  float4* stage4 = reinterpret_cast<float4*>(p.stage) + (size_t)blockIdx.x * (ROWS * DH / 4);
   // A point whose NS rows straddle lanes 31|32 (NS not a divisor of 32) has its first `rem` rows in
   // the lower warp and the other NS-rem in the partner warp (same columns, next TMEM quadrant):
   // the upper warp pre-sums its rows and hands one value per column over through the idle S_x.
@@ -869,9 +777,8 @@ __device__ __noinline__ long long pool_tile(const Params& p, Ctx cx, const Epi e
         }
         asm volatile("bar.sync %0, 64;" ::"r"(2 + pair_id) : "memory");
       }
-      // x3[tileB][ctaB][nb][h][jq (32)][row (64)][4]
-      float4* dst = reinterpret_cast<float4*>(p.x3) +
-                    ((((tb * 2 + cb) * 2 + nb) * 2 + e.h) * 32 + (e.cs * 16 + half * 8)) * 64 + rb_;
+      // stage[cta][nb][h][jq (32)][row (64)][4]
+      float4* dst = stage4 + ((nb * 2 + e.h) * 32 + (e.cs * 16 + half * 8)) * 64 + rb_;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float s4[4];
@@ -910,10 +817,131 @@ __device__ __noinline__ long long pool_tile(const Params& p, Ctx cx, const Epi e
 }
 
 // =============================================================================================
-// Phase A
+// B-tile pieces of the epilogue warps (executed once per group: kept out of line so that the A-tile
+// loop, which runs nA times as often, keeps a small instruction footprint)
+// =============================================================================================
+constexpr int OFF_WOUT = OFF_SX;                       // lin_out weights [4][512] + bias [4] (fp32), during the head
+constexpr int OFF_PART = OFF_SX + 8704;                // [4 outputs][4 column parts][64 rows] partial sums
+
+// pooled rows of this CTA's staging buffer -> TMEM residual at column `xc` (fp32) and, with `to_sx`,
+// relu -> bf16 operand in S_x (publishing the 8 K slices)
+__device__ __noinline__ void load_x_tile(const Params& p, const Ctx cx, const Epi e, uint32_t xc, bool valid, bool to_sx) {
+  const float4* stage4 = reinterpret_cast<const float4*>(p.stage) + (size_t)blockIdx.x * (ROWS * DH / 4);
+#pragma unroll 1
+  for (int nb = 0; nb < 2; ++nb) {
+    const float4* src = stage4 + ((nb * 2 + e.h) * 32 + e.cs * 16) * 64 + e.row;
+    float4 t[16];  // both 32-column halves in flight: the loads are L2 round trips (.cg: written by this CTA)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) t[j] = valid ? __ldcg(src + (size_t)j * 64) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t r[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        r[4 * j] = __float_as_uint(t[half * 8 + j].x);
+        r[4 * j + 1] = __float_as_uint(t[half * 8 + j].y);
+        r[4 * j + 2] = __float_as_uint(t[half * 8 + j].z);
+        r[4 * j + 3] = __float_as_uint(t[half * 8 + j].w);
+      }
+      tmem_st32(cx.tmem + e.lane_addr + xc + nb * 128 + e.cs * 64 + half * 32, r);
+      if (to_sx) {
+        const int f0 = feat0(e, nb, half);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t kg = (uint32_t)(f0 >> 3) + j;
+          uint32_t addr = cx.smem + OFF_SX + kg * (ROWS * 16) + e.row * 16;
+          auto rl = [&](int i) { return fmaxf(__uint_as_float(r[8 * j + i]), 0.f); };
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(rl(0), rl(1))),
+                       "r"(pack_bf16x2(rl(2), rl(3))), "r"(pack_bf16x2(rl(4), rl(5))), "r"(pack_bf16x2(rl(6), rl(7)))
+                       : "memory");
+        }
+      }
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (to_sx && e.lane == 0) mbar_arrive_cluster(cx.bar(SX_READY + nb * 4 + e.h * 2 + e.cs), 0);
+  }
+}
+
+// lin_out(relu(x)) on CUDA cores from the fp32 residual in TMEM + sigmoid/relu head
+// (src/model/resnetfc.py:234-235, models.py.backup2:274-281); `gp` = this thread's output point (< 0: none)
+__device__ __noinline__ void head_tile(const Params& p, Ctx cx, const Epi e, uint32_t xcol, uint32_t xph, bool wait_x,
+                                       long long gp_row, uint8_t* smem_raw) {
+  float* s_wout = reinterpret_cast<float*>(smem_raw + OFF_WOUT);
+  float* s_part = reinterpret_cast<float*>(smem_raw + OFF_PART);
+  const float* biasB = reinterpret_cast<const float*>(p.w + p.off_biasB);
+  const float* bO = biasB + (size_t)p.n_post * DH;
+  const int warp = threadIdx.x >> 5, lane = e.lane;
+  {  // S_x is idle (the last fc_0 has completed): stage the head weights there
+    const float4* wo = reinterpret_cast<const float4*>(p.w + p.off_lin_out);
+    const int t = threadIdx.x - 128;  // 256 epilogue threads
+    for (int i = t; i < (4 * DH + 4) / 4; i += 256) reinterpret_cast<float4*>(s_wout)[i] = __ldg(wo + i);
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int nb = 0; nb < 2; ++nb) {
+    BiasRegs bo;
+    prefetch_bias(bo, e, bO, nb);
+    if (wait_x) {
+      mbar_wait(cx.bar(X_READY + nb), xph, cx.err, 505);
+      tc_fence_after();
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t r[32];
+      tmem_ld32(cx.tmem + e.lane_addr + xcol + nb * 128 + e.cs * 64 + half * 32, r);
+      tmem_ld_wait();
+      if (nb == 1 && half == 1) {  // X is in registers: the next tile may reuse its TMEM half
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(cx.bar(XP_DONE), 0);
+      }
+      const int f0 = feat0(e, nb, half);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 bb = bo.v[half * 8 + j];
+        const float xs[4] = {fmaxf(__uint_as_float(r[4 * j + 0]) + bb.x, 0.f), fmaxf(__uint_as_float(r[4 * j + 1]) + bb.y, 0.f),
+                             fmaxf(__uint_as_float(r[4 * j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(r[4 * j + 3]) + bb.w, 0.f)};
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {  // one 128-bit broadcast read per (output, 4 features)
+          const float4 w4 = *reinterpret_cast<const float4*>(s_wout + o * DH + f0 + 4 * j);
+          part[o] = fmaf(xs[0], w4.x, part[o]);
+          part[o] = fmaf(xs[1], w4.y, part[o]);
+          part[o] = fmaf(xs[2], w4.z, part[o]);
+          part[o] = fmaf(xs[3], w4.w, part[o]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 4; ++o) s_part[(o * 4 + e.h * 2 + e.cs) * 64 + e.row] = part[o];
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (warp < 6) {  // 64 threads: one per row (warps 4, 5 hold rows 0..63 in e.row order)
+    const int row = (warp - 4) * 32 + lane;
+    if (gp_row >= 0) {
+      float o4[4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        float s = s_wout[4 * DH + o];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s += s_part[(o * 4 + q) * 64 + row];
+        if (p.apply_head) s = (o < 3) ? 1.f / (1.f + __expf(-s)) : fmaxf(s, 0.f);
+        o4[o] = s;
+      }
+      reinterpret_cast<float4*>(p.out)[gp_row] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+    }
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");  // s_wout / s_part (= S_x) may be overwritten from here on
+}
+
+// =============================================================================================
+// The fused kernel
 // =============================================================================================
 template <bool SM>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phaseA_kernel(const __grid_constant__ Params p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Ctx cx;
   cx.smem = smem_u32(smem_raw);
@@ -939,6 +967,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
   cx.tmem = *tmem_slot;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int nsl = p.nks_z + p.nks_c;
+  // A tile `tile` closes its group when it is the nA-th of the group or the pair's last tile
+#define PNR_GROUP_END(k_, tile_) ((k_) == p.nA || (tile_) + npairs >= p.tilesA)
 
   if (warp == 0) {
     // ===================== producer =====================
@@ -946,6 +976,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
       Ring rb;
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), PNR_RING_A);
       uint32_t git = 0;
+      int k = 0;
       for (int tile = pair; tile < p.tilesA; tile += npairs, ++git) {
         if (p.fused_gather) {  // this CTA's rows of the tile have been gathered (and are visible to TMA)
           twait(cx, 1, cx.bar(ZC_READY), git & 1, 203);
@@ -971,6 +1002,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
           for (int c = 0; c < 16; ++c)  // same quartered order as gemm_fc1: (sh, nb, s4) = (c/8, (c/4)%2, c%4)
             load_b(cx, rb, &p.tm_w, wchunk(p.off_g3[b], (c >> 3) * 4 + (c & 3), (c >> 2) & 1, cx.rank));
         }
+        if (++k, PNR_GROUP_END(k, tile)) {  // ---- B tile of the group
+          k = 0;
+          for (int j = 0; j < p.n_post; ++j) {
+            const int b = p.n_pre + j;
+#pragma unroll 1
+            for (int c = 0; c < 2 * (DH / KS); ++c)
+              load_b(cx, rb, &p.tm_w, wchunk(p.off_g2[b], c % (DH / KS), c / (DH / KS), cx.rank));
+#pragma unroll 1
+            for (int c = 0; c < 16; ++c)
+              load_b(cx, rb, &p.tm_w, wchunk(p.off_g3[b], (c >> 3) * 4 + (c & 3), (c >> 2) & 1, cx.rank));
+          }
+        }
       }
       if (p.stats && cx.rank == 0 && lane == 0) {
         unsigned long long* st = p.stats + (size_t)pair * 16;
@@ -985,28 +1028,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
     if (cx.rank == 0 && mma_enter<SM>()) {
       Ring rb;
       rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), PNR_RING_A);
-      uint32_t use = 0;  // (tile-local block counter) parity source for SX/H barriers
-      uint32_t it = 0;
-      for (int tile = pair; tile < p.tilesA; tile += npairs, ++it) {
-        const uint32_t xcol = (it & 1) ? 256u : 0u, netcol = 256u - xcol;
-        gemm_from_ring<SM>(cx, rb, nsl, xcol, true);
-        // The previous tile's pool must have consumed its X_READY completions before they are
-        // signalled again (a waiter that misses one completion of a 1-count mbarrier waits for
-        // ever), and it must have finished reading the old X before fc_0 reuses it as NET.
-        if (it > 0) twait(cx, 4, cx.bar(XP_DONE), (it - 1) & 1, 330);
-        signal<SM>(cx, X_READY);
-        signal<SM>(cx, X_READY + 1);
-        for (int b = 0; b < p.n_pre; ++b, ++use) {
-          gemm_fc0<SM>(cx, rb, netcol, use & 1);
-          if (b + 1 < p.n_pre) gemm_from_ring<SM>(cx, rb, p.nks_z, xcol, false);
-          gemm_fc1<SM>(cx, rb, xcol, use & 1);
+      uint32_t use = 0;  // block counter: parity source of the SX/H barriers
+      uint32_t tc = 0;   // tile counter (A and B tiles): X/NET halves swap every tile; XP_DONE parity
+      int k = 0;
+      for (int tile = pair; tile < p.tilesA; tile += npairs) {
+        {
+          const uint32_t xcol = (tc & 1) ? 256u : 0u, netcol = 256u - xcol;
+          gemm_from_ring<SM>(cx, rb, nsl, xcol, true);
+          // The previous tile's pool / head must have consumed its X_READY completions before they are
+          // signalled again (a waiter that misses one completion of a 1-count mbarrier waits for
+          // ever), and it must have finished reading the old X before fc_0 reuses it as NET.
+          if (tc > 0) twait(cx, 4, cx.bar(XP_DONE), (tc - 1) & 1, 330);
+          signal<SM>(cx, X_READY);
+          signal<SM>(cx, X_READY + 1);
+          for (int b = 0; b < p.n_pre; ++b, ++use) {
+            gemm_fc0<SM>(cx, rb, netcol, use & 1);
+            if (b + 1 < p.n_pre) gemm_from_ring<SM>(cx, rb, p.nks_z, xcol, false);
+            gemm_fc1<SM>(cx, rb, xcol, use & 1);
+          }
+          ++tc;
+        }
+        if (++k, PNR_GROUP_END(k, tile)) {  // ---- B tile: X was loaded by the epilogue warps (SX_READY)
+          k = 0;
+          const uint32_t xcol = (tc & 1) ? 256u : 0u, netcol = 256u - xcol;
+          twait(cx, 4, cx.bar(XP_DONE), (tc - 1) & 1, 530);  // the pool has read the A tile's X (= this NET half)
+          for (int j = 0; j < p.n_post; ++j, ++use) {
+            gemm_fc0<SM>(cx, rb, netcol, use & 1);
+            gemm_fc1<SM>(cx, rb, xcol, use & 1);
+          }
+          ++tc;
         }
       }
       if (p.stats && cx.rank == 0 && lane == 0) {
         unsigned long long* st = p.stats + (size_t)pair * 16;
         st[0] = clock64() - t_begin;
         for (int i = 0; i < 5; ++i) st[1 + i] = cx.w[i];
-        p.stats[74 * 16 + pair] = cx.w[5];  // sum of issue -> full-observed latencies
       }
     }
   } else if (warp < 4) {
@@ -1039,257 +1095,95 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
     // ===================== epilogue =====================
     const Epi e = make_epi(warp, lane);
     const float* biasA = reinterpret_cast<const float*>(p.w + p.off_biasA);
+    const float* biasB = reinterpret_cast<const float*>(p.w + p.off_biasB);
     const float* bias0 = reinterpret_cast<const float*>(p.w + p.off_bias0);
-    uint32_t xph = 0, nph = 0, it = 0;
-    for (int tile = pair; tile < p.tilesA; tile += npairs, ++it) {
-      const uint32_t xcol = (it & 1) ? 256u : 0u, netcol = 256u - xcol;
-      for (int b = 0; b < p.n_pre; ++b) {
-        long long t0 = 0;
-        BiasRegs br;
-        for (int nb = 0; nb < 2; ++nb) {
-          prefetch_bias(br, e, biasA + (size_t)b * DH, nb);
-          twait(cx, 0, cx.bar(X_READY + nb), xph, 401 + nb * 1000 + (int)it * 10000 + warp * 1000000 + (int)cx.rank * 100000000);
-          tc_fence_after();
-          t0 = clock64();
-          epi_to_operand(cx, e, xcol, nb, br, OFF_SX, SX_READY);
-          cx.w[2] += clock64() - t0;
+    uint32_t xph = 0, nph = 0, tc = 0;
+    int k = 0, group_tile0 = pair;
+    for (int tile = pair; tile < p.tilesA; tile += npairs) {
+      {
+        const uint32_t xcol = (tc & 1) ? 256u : 0u, netcol = 256u - xcol;
+        for (int b = 0; b < p.n_pre; ++b) {
+          long long t0 = 0;
+          BiasRegs br;
+          for (int nb = 0; nb < 2; ++nb) {
+            prefetch_bias(br, e, biasA + (size_t)b * DH, nb);
+            twait(cx, 0, cx.bar(X_READY + nb), xph, 401 + nb * 1000 + (int)tc * 10000 + warp * 1000000 + (int)cx.rank * 100000000);
+            tc_fence_after();
+            t0 = clock64();
+            epi_to_operand(cx, e, xcol, nb, br, OFF_SX, SX_READY);
+            cx.w[2] += clock64() - t0;
+          }
+          xph ^= 1;
+          for (int nb = 0; nb < 2; ++nb) {
+            prefetch_bias(br, e, bias0 + (size_t)b * DH, nb);
+            twait(cx, 1, cx.bar(NET_READY + nb), nph, 402 + nb);
+            tc_fence_after();
+            t0 = clock64();
+            epi_to_operand(cx, e, netcol, nb, br, OFF_H, H_READY);
+            cx.w[3] += clock64() - t0;
+          }
+          nph ^= 1;
         }
+        // ---- view mean-pool of the residual stream -> pooled x (fp32) rows k*ppw.. of the staging buffer ----
+        long long tp;
+        const int krow0 = k * p.ppw;
+        switch (p.ns) {
+          case 1: tp = pool_tile<1>(p, cx, e, tile, krow0, xcol, xph, tc, smem_raw); break;
+          case 2: tp = pool_tile<2>(p, cx, e, tile, krow0, xcol, xph, tc, smem_raw); break;
+          case 3: tp = pool_tile<3>(p, cx, e, tile, krow0, xcol, xph, tc, smem_raw); break;
+          case 4: tp = pool_tile<4>(p, cx, e, tile, krow0, xcol, xph, tc, smem_raw); break;
+          default: tp = pool_tile<0>(p, cx, e, tile, krow0, xcol, xph, tc, smem_raw); break;
+        }
+        cx.w[4] += tp;  // pool work only (waits excluded)
         xph ^= 1;
-        for (int nb = 0; nb < 2; ++nb) {
-          prefetch_bias(br, e, bias0 + (size_t)b * DH, nb);
-          twait(cx, 1, cx.bar(NET_READY + nb), nph, 402 + nb);
-          tc_fence_after();
-          t0 = clock64();
-          epi_to_operand(cx, e, netcol, nb, br, OFF_H, H_READY);
-          cx.w[3] += clock64() - t0;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(cx.bar(XP_DONE), 0);
+        ++tc;
+      }
+      if (++k, PNR_GROUP_END(k, tile)) {
+        // ===== B tile: the group's pooled points (row r = kk*ppw + pl <-> A tile group_tile0 + kk*npairs) =====
+        const uint32_t xcol = (tc & 1) ? 256u : 0u, netcol = 256u - xcol;
+        const int kk = e.row / p.ppw, pl = e.row - kk * p.ppw;
+        const long long gp = (long long)((group_tile0 + kk * npairs) * 2 + (int)cx.rank) * p.ppw + pl;
+        const bool valid = kk < k && gp < p.P;
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // all pooled rows of this CTA are written
+        load_x_tile(p, cx, e, xcol, valid, p.n_post > 0);
+        for (int j = 0; j < p.n_post; ++j) {
+          const int b = p.n_pre + j;
+          BiasRegs br;
+          for (int nb = 0; nb < 2; ++nb) {
+            prefetch_bias(br, e, bias0 + (size_t)b * DH, nb);
+            twait(cx, 1, cx.bar(NET_READY + nb), nph, 502 + nb);
+            tc_fence_after();
+            epi_to_operand(cx, e, netcol, nb, br, OFF_H, H_READY);
+          }
+          nph ^= 1;
+          if (j + 1 < p.n_post) {
+            for (int nb = 0; nb < 2; ++nb) {
+              prefetch_bias(br, e, biasB + (size_t)(j + 1) * DH, nb);
+              twait(cx, 0, cx.bar(X_READY + nb), xph, 501);
+              tc_fence_after();
+              epi_to_operand(cx, e, xcol, nb, br, OFF_SX, SX_READY);
+            }
+            xph ^= 1;
+          }
         }
-        nph ^= 1;
+        // output row of the 64 row-owner threads (warps 4, 5; their e.row = (warp-4)*32 + lane)
+        head_tile(p, cx, e, xcol, xph, p.n_post > 0, valid ? gp : -1, smem_raw);
+        if (p.n_post > 0) xph ^= 1;
+        ++tc;
+        k = 0;
+        group_tile0 = tile + npairs;
       }
-      // ---- view mean-pool of the residual stream -> pooled x (fp32) in phase-B tile order ----
-      long long tp;
-      switch (p.ns) {
-        case 1: tp = pool_tile<1>(p, cx, e, tile, xcol, xph, it, smem_raw); break;
-        case 2: tp = pool_tile<2>(p, cx, e, tile, xcol, xph, it, smem_raw); break;
-        case 3: tp = pool_tile<3>(p, cx, e, tile, xcol, xph, it, smem_raw); break;
-        case 4: tp = pool_tile<4>(p, cx, e, tile, xcol, xph, it, smem_raw); break;
-        default: tp = pool_tile<0>(p, cx, e, tile, xcol, xph, it, smem_raw); break;
-      }
-      cx.w[4] += tp;  // pool work only (waits excluded)
-      xph ^= 1;
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(cx.bar(XP_DONE), 0);
     }
     if (p.stats && cx.rank == 0 && warp == 4 && lane == 0) {
       unsigned long long* st = p.stats + (size_t)pair * 16;
       st[9] = clock64() - t_begin;
       for (int i = 0; i < 5; ++i) st[10 + i] = cx.w[i];
-#if PNR_TC_STATS
-      p.stats[74 * 18 + pair] = it;  // tiles this pair processed
-#endif
     }
   }
-  __syncwarp();
-  tc_fence_before();
-  cluster_sync();
-  if (warp == 2) tmem_dealloc<2>(cx.tmem, 512);
-}
-
-// =============================================================================================
-// Phase B
-// =============================================================================================
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phaseB_kernel(const __grid_constant__ Params p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  Ctx cx;
-  cx.smem = smem_u32(smem_raw);
-  cx.bars = cx.smem + OFF_BARS;
-  cx.rank = cluster_ctarank();
-  cx.err = p.err;
-  for (int i = 0; i < 6; ++i) cx.w[i] = 0;
-  const long long t_begin = clock64();
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + OFF_BARS + N_BARS * 8);
-  float* s_wout = reinterpret_cast<float*>(smem_raw + OFF_LINOUT);          // [4][512] + [4]
-  float* s_part = s_wout + 4 * DH + 4;                                    // [4 outputs][4 parts][64 rows]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) setup_barriers(cx);
-  if (warp == 2) {
-    tmem_alloc<2>(smem_u32(tmem_slot), 512);
-    tmem_relinquish<2>();
-  }
-  {
-    const float* wo = reinterpret_cast<const float*>(p.w + p.off_lin_out);
-    for (int i = threadIdx.x; i < 4 * DH + 4; i += blockDim.x) s_wout[i] = wo[i];
-  }
-  __syncthreads();
-  tc_fence_before();
-  cluster_sync();
-  tc_fence_after();
-  cx.tmem = *tmem_slot;
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  // X and NET swap TMEM halves from tile to tile: the next tile's pooled x is loaded into the NET
-  // half (and S_x) while the last fc_1 of the current tile still runs, so only the read of the final
-  // X (not the x3 load) separates two tiles on the tensor pipe.
-
-  if (warp == 0) {
-    if (PROD_ENTER()) {
-      Ring rb;
-      rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST_B);
-      for (int tile = pair; tile < p.tilesB; tile += npairs)
-        for (int j = 0; j < p.n_post; ++j) {
-          const int b = p.n_pre + j;
-#pragma unroll 1
-          for (int c = 0; c < 2 * (DH / KS); ++c)  // nb-outer, s-inner
-            load_b(cx, rb, &p.tm_w, wchunk(p.off_g2[b], c % (DH / KS), c / (DH / KS), cx.rank));
-#pragma unroll 1
-          for (int c = 0; c < 16; ++c)  // same quartered order as gemm_fc1: (sh, nb, s4) = (c/8, (c/4)%2, c%4)
-            load_b(cx, rb, &p.tm_w, wchunk(p.off_g3[b], (c >> 3) * 4 + (c & 3), (c >> 2) & 1, cx.rank));
-        }
-    }
-  } else if (warp == 1) {
-    if (cx.rank == 0 && mma_enter<true>()) {
-      Ring rb;
-      rb.init(cx.bar(B_FULL), cx.bar(B_EMPTY), NB_ST_B);
-      uint32_t use = 0, it = 0;
-      for (int tile = pair; tile < p.tilesB; tile += npairs, ++it) {
-        const uint32_t xcol = (it & 1) ? 256u : 0u, netcol = 256u - xcol;
-        // NET of this tile is the X of the previous one: its head epilogue must have read it
-        if (it > 0 && p.n_post > 0) twait(cx, 4, cx.bar(XP_DONE), (it - 1) & 1, 530);
-        for (int j = 0; j < p.n_post; ++j, ++use) {
-          gemm_fc0<true>(cx, rb, netcol, use & 1);
-          gemm_fc1<true>(cx, rb, xcol, use & 1);
-        }
-      }
-    }
-  } else if (warp >= 4) {
-    const Epi e = make_epi(warp, lane);
-    const float* biasB = reinterpret_cast<const float*>(p.w + p.off_biasB);
-    const float* bias0 = reinterpret_cast<const float*>(p.w + p.off_bias0);
-    // pooled x of `tile`: fp32 -> TMEM residual at column `xc`, relu -> bf16 operand in S_x
-    auto load_x = [&](int tile, uint32_t xc) {
-      const bool valid = (long long)tile * 128 + cx.rank * 64 + e.row < p.P;
-#pragma unroll 1
-      for (int nb = 0; nb < 2; ++nb) {
-        const float4* src = reinterpret_cast<const float4*>(p.x3) +
-                            (((((long long)tile * 2 + cx.rank) * 2 + nb) * 2 + e.h) * 32 + e.cs * 16) * 64 + e.row;
-        float4 t[16];  // both 32-column halves in flight: the loads are L2 round trips
-#pragma unroll
-        for (int j = 0; j < 16; ++j) t[j] = valid ? __ldg(src + (size_t)j * 64) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t r[32];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            r[4 * j] = __float_as_uint(t[half * 8 + j].x);
-            r[4 * j + 1] = __float_as_uint(t[half * 8 + j].y);
-            r[4 * j + 2] = __float_as_uint(t[half * 8 + j].z);
-            r[4 * j + 3] = __float_as_uint(t[half * 8 + j].w);
-          }
-          tmem_st32(cx.tmem + e.lane_addr + xc + nb * 128 + e.cs * 64 + half * 32, r);
-          const int f0 = feat0(e, nb, half);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t kg = (uint32_t)(f0 >> 3) + j;
-            uint32_t addr = cx.smem + OFF_SX + kg * (ROWS * 16) + e.row * 16;
-            auto rl = [&](int i) { return fmaxf(__uint_as_float(r[8 * j + i]), 0.f); };
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(rl(0), rl(1))),
-                         "r"(pack_bf16x2(rl(2), rl(3))), "r"(pack_bf16x2(rl(4), rl(5))), "r"(pack_bf16x2(rl(6), rl(7)))
-                         : "memory");
-          }
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (p.n_post > 0 && lane == 0) mbar_arrive_cluster(cx.bar(SX_READY + nb * 4 + e.h * 2 + e.cs), 0);
-      }
-    };
-    uint32_t xph = 0, nph = 0, it = 0;
-    if (pair < p.tilesB) load_x(pair, 0u);
-    for (int tile = pair; tile < p.tilesB; tile += npairs, ++it) {
-      const uint32_t xcol = (it & 1) ? 256u : 0u, netcol = 256u - xcol;
-      for (int j = 0; j < p.n_post; ++j) {
-        const int b = p.n_pre + j;
-        BiasRegs br;
-        for (int nb = 0; nb < 2; ++nb) {
-          prefetch_bias(br, e, bias0 + (size_t)b * DH, nb);
-          mbar_wait(cx.bar(NET_READY + nb), nph, cx.err, 502 + nb);
-          tc_fence_after();
-          epi_to_operand(cx, e, netcol, nb, br, OFF_H, H_READY);
-        }
-        nph ^= 1;
-        if (j + 1 < p.n_post) {
-          for (int nb = 0; nb < 2; ++nb) {
-            prefetch_bias(br, e, biasB + (size_t)(j + 1) * DH, nb);
-            mbar_wait(cx.bar(X_READY + nb), xph, cx.err, 501);
-            tc_fence_after();
-            epi_to_operand(cx, e, xcol, nb, br, OFF_SX, SX_READY);
-          }
-          xph ^= 1;
-        }
-      }
-      // NET and S_x are idle from here on (the last fc_0 has been consumed): next tile's x goes there
-      // while the last fc_1 runs
-      if (tile + npairs < p.tilesB) load_x(tile + npairs, netcol);
-      // ---- lin_out(relu(x)) + head ----
-      const float* bO = biasB + (size_t)p.n_post * DH;
-      float part[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int nb = 0; nb < 2; ++nb) {
-        BiasRegs bo;
-        prefetch_bias(bo, e, bO, nb);
-        if (p.n_post > 0) {
-          mbar_wait(cx.bar(X_READY + nb), xph, cx.err, 505);
-          tc_fence_after();
-        }
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t r[32];
-          tmem_ld32(cx.tmem + e.lane_addr + xcol + nb * 128 + e.cs * 64 + half * 32, r);
-          tmem_ld_wait();
-          if (nb == 1 && half == 1) {  // X is in registers: the next tile's fc_0 may overwrite it
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(cx.bar(XP_DONE), 0);
-          }
-          const int f0 = feat0(e, nb, half);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bb = bo.v[half * 8 + j];
-            const float xs[4] = {fmaxf(__uint_as_float(r[4 * j + 0]) + bb.x, 0.f), fmaxf(__uint_as_float(r[4 * j + 1]) + bb.y, 0.f),
-                                 fmaxf(__uint_as_float(r[4 * j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(r[4 * j + 3]) + bb.w, 0.f)};
-#pragma unroll
-            for (int o = 0; o < 4; ++o) {  // one 128-bit broadcast read per (output, 4 features)
-              const float4 w4 = *reinterpret_cast<const float4*>(s_wout + o * DH + f0 + 4 * j);
-              part[o] = fmaf(xs[0], w4.x, part[o]);
-              part[o] = fmaf(xs[1], w4.y, part[o]);
-              part[o] = fmaf(xs[2], w4.z, part[o]);
-              part[o] = fmaf(xs[3], w4.w, part[o]);
-            }
-          }
-        }
-      }
-      if (p.n_post > 0) xph ^= 1;
-#pragma unroll
-      for (int o = 0; o < 4; ++o) s_part[(o * 4 + e.h * 2 + e.cs) * 64 + e.row] = part[o];
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (warp < 6) {  // 64 threads: one per row
-        const int row = (warp - 4) * 32 + lane;
-        const long long g = (long long)tile * 128 + cx.rank * 64 + row;
-        if (g < p.P) {
-          float o4[4];
-#pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            float s = s_wout[4 * DH + o];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) s += s_part[(o * 4 + q) * 64 + row];
-            if (p.apply_head) s = (o < 3) ? 1.f / (1.f + __expf(-s)) : fmaxf(s, 0.f);
-            o4[o] = s;
-          }
-          reinterpret_cast<float4*>(p.out)[g] = make_float4(o4[0], o4[1], o4[2], o4[3]);
-        }
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-    }
-  }
+#undef PNR_GROUP_END
   __syncwarp();
   tc_fence_before();
   cluster_sync();
@@ -1299,23 +1193,83 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_phas
 // =============================================================================================
 // host side
 // =============================================================================================
+// Per-device state: the barrier-fault word (mapped pinned host memory, so the tag survives a trap), the SM
+// count, and whether the kernels' dynamic shared-memory attribute has been raised.  Guarded by one mutex;
+// everything else in this file is stateless or thread-local.
+struct DeviceState {
+  int* err_host = nullptr;  // [0] fault tag (0 = none), [1] wait timeout in ms (0 = never give up)
+  int* err_dev = nullptr;
+  int sms = 0;
+  bool attr_set[2] = {false, false};
+};
+static std::mutex g_dev_mutex;
+static DeviceState g_dev[PNR_MAX_DEVICES];
+
+static int wait_timeout_ms() {
+  static const int ms = [] {  // PNR_WAIT_TIMEOUT_MS: 0 disables the trap (debuggers, compute-sanitizer, time-slicing)
+    const char* e = getenv("PNR_WAIT_TIMEOUT_MS");
+    return e ? atoi(e) : 2000;
+  }();
+  return ms < 0 ? 0 : ms;
+}
+
+static int device_state(DeviceState** out) {
+  int dev = 0;
+  PNR_CUDA(cudaGetDevice(&dev));
+  PNR_CHECK_ARG(dev >= 0 && dev < PNR_MAX_DEVICES, "device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  DeviceState& d = g_dev[dev];
+  if (!d.err_host) {
+    int* h = nullptr;
+    PNR_CUDA(cudaHostAlloc((void**)&h, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+    h[0] = 0;
+    h[1] = wait_timeout_ms();
+    PNR_CUDA(cudaHostGetDevicePointer((void**)&d.err_dev, h, 0));
+    PNR_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+    if (d.sms <= 0) d.sms = 148;
+    d.err_host = h;
+  }
+  *out = &d;
+  return PNR_OK;
+}
+
+// a fault recorded by an earlier launch on this device is reported (once) by the next call
+static int take_fault(DeviceState& d, const char* when) {
+  int v = *(volatile int*)d.err_host;
+  if (v == 0) return PNR_OK;
+  d.err_host[0] = 0;
+  set_err("tensor-core MLP pipeline: a barrier wait timed out in an earlier launch on this device (tag %d; %s); "
+          "its results are invalid", v, when);
+  return PNR_ERR_CUDA;
+}
+
 struct Plan {
-  int ppw, ptile, tilesA, tilesB, nsl;
+  int ppw, ptile, tilesA, nA, nsl, pairs, zc_slots;
   uint8_t* zc;
-  float* x3;
+  float* stage;
   size_t total;
 };
 
-static Plan make_plan(const Layout& L, int ns, long long P, void* ws, size_t ws_bytes) {
+static int pairs_for(int sms, int tiles) {
+  int pairs = sms / 2;
+  static int cap = [] { const char* e = getenv("PNR_MAX_PAIRS"); return e ? atoi(e) : 0; }();  // experiment knob
+  if (cap > 0 && cap < pairs) pairs = cap;
+  return tiles < pairs ? (tiles > 0 ? tiles : 1) : pairs;
+}
+
+// `ring`: the operand image is produced inside the kernel (gather warps) and needs only 3 slots per pair
+static Plan make_plan(const Layout& L, int sms, int ns, long long P, bool ring, void* ws, size_t ws_bytes) {
   Plan pl;
   pl.ppw = 64 / ns;
   pl.ptile = 2 * pl.ppw;
+  pl.nA = 64 / pl.ppw;
   pl.tilesA = (int)ceil_div_ll(P, pl.ptile);
-  pl.tilesB = (int)ceil_div_ll(P, 128);
   pl.nsl = L.nks_z + L.nks_c;
+  pl.pairs = pairs_for(sms, pl.tilesA);
+  pl.zc_slots = (ring && pl.tilesA > 3 * pl.pairs) ? 3 * pl.pairs : pl.tilesA;
   Arena a(ws, ws_bytes);
-  pl.zc = a.take<uint8_t>((size_t)pl.tilesA * 2 * pl.nsl * A_SLICE);
-  pl.x3 = a.take<float>((size_t)pl.tilesB * 128 * DH);
+  pl.zc = a.take<uint8_t>((size_t)pl.zc_slots * 2 * pl.nsl * A_SLICE);
+  pl.stage = a.take<float>((size_t)pl.pairs * 2 * ROWS * DH);
   pl.total = a.off + 256;
   return pl;
 }
@@ -1354,8 +1308,43 @@ static int encode_rows256(CUtensorMap* tm, const void* base, size_t bytes, int b
   return PNR_OK;
 }
 
-static int launch_cluster(void (*kern)(const Params), int pairs, const Params& p, cudaStream_t st) {
-  PNR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+// The two tensor maps of a launch depend only on (base, bytes, box): encoded once per distinct operand
+// image / scratch range and thread, not per launch.
+struct TmapKey {
+  const void* base;
+  size_t bytes;
+  int box_rows;
+};
+static int cached_tmap(CUtensorMap* out, const void* base, size_t bytes, int box_rows) {
+  struct Entry {
+    TmapKey k;
+    CUtensorMap tm;
+  };
+  static thread_local Entry cache[8];
+  static thread_local int used = 0, next = 0;
+  for (int i = 0; i < used; ++i)
+    if (cache[i].k.base == base && cache[i].k.bytes == bytes && cache[i].k.box_rows == box_rows) {
+      *out = cache[i].tm;
+      return PNR_OK;
+    }
+  PNR_TRY(encode_rows256(out, base, bytes, box_rows));
+  Entry& e = cache[next];
+  e.k = TmapKey{base, bytes, box_rows};
+  e.tm = *out;
+  next = (next + 1) % 8;
+  if (used < 8) ++used;
+  return PNR_OK;
+}
+
+static int launch_cluster(DeviceState& d, bool solo, int pairs, const Params& p, cudaStream_t st) {
+  void (*kern)(const Params) = solo ? mlp_fused_kernel<true> : mlp_fused_kernel<false>;
+  {
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    if (!d.attr_set[solo ? 1 : 0]) {
+      PNR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      d.attr_set[solo ? 1 : 0] = true;
+    }
+  }
   cudaLaunchConfig_t cfg;
   memset((void*)&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * pairs);
@@ -1367,28 +1356,15 @@ static int launch_cluster(void (*kern)(const Params), int pairs, const Params& p
   return PNR_OK;
 }
 
-static int num_pairs(int tiles) {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  int pairs = sms / 2;
-  static int cap = [] { const char* e = getenv("PNR_MAX_PAIRS"); return e ? atoi(e) : 0; }();  // experiment knob
-  if (cap > 0 && cap < pairs) pairs = cap;
-  return tiles < pairs ? tiles : pairs;
-}
-
 struct GatherArgs {
   const pnr_scene* sc;
   const float *xyz, *viewdirs, *rays, *z;
   int K;
 };
 
-static int run_phases(const pnr_mlp& m, const Layout& L, const Plan& pl, int ns, long long P, float* out, int head,
-                      cudaStream_t st, const GatherArgs* ga = nullptr) {
+static int run_fused(DeviceState& d, const pnr_mlp& m, const Layout& L, const Plan& pl, int ns, long long P, float* out,
+                     int head, cudaStream_t st, const GatherArgs* ga = nullptr) {
+  PNR_TRY(take_fault(d, "reported before the next launch"));
   // algorithmic work (2*MACs of the nn.Linear layers, unpadded)
   const double mac_pre = (double)m.d_in * DH + (double)L.n_pre * m.d_latent * DH + 2.0 * L.n_pre * DH * DH;
   const double mac_post = 2.0 * L.n_post * DH * DH + (double)DH * m.d_out;
@@ -1410,17 +1386,16 @@ static int run_phases(const pnr_mlp& m, const Layout& L, const Plan& pl, int ns,
   p.nks_c = L.nks_c;
   p.ns = ns;
   p.ppw = pl.ppw;
+  p.nA = pl.nA;
   p.P = P;
   p.tilesA = pl.tilesA;
-  p.tilesB = pl.tilesB;
   p.zc = pl.zc;
-  p.x3 = pl.x3;
+  p.stage = pl.stage;
   p.out = out;
   p.apply_head = head;
   if (ga) {
     p.fused_gather = 1;
-    // the scratch holds one slot per tile: use it as a 3-deep ring per pair only when that needs fewer slots
-    p.zc_ring = (pl.tilesA > 3 * num_pairs(pl.tilesA)) ? 3 : 0;
+    p.zc_ring = (pl.zc_slots < pl.tilesA) ? 3 : 0;  // 3-deep ring per pair unless one slot per tile is smaller
     p.sc = *ga->sc;
     p.xyz = ga->xyz;
     p.viewdirs = ga->viewdirs;
@@ -1428,30 +1403,29 @@ static int run_phases(const pnr_mlp& m, const Layout& L, const Plan& pl, int ns,
     p.zsamp = ga->z;
     p.K = ga->K;
   }
-  PNR_TRY(ensure_err_word());
-  p.err = g_err_dev;
+  p.err = d.err_dev;
   p.stats = g_stats_ptr;
-  PNR_TRY(encode_rows256(&p.tm_w, m.packed, L.total, B_CHUNK / B_SPLIT / 256));
-  PNR_TRY(encode_rows256(&p.tm_zc, pl.zc, (size_t)pl.tilesA * 2 * pl.nsl * A_SLICE, A_SLICE / A_SPLIT / 256));
+  PNR_TRY(cached_tmap(&p.tm_w, m.packed, L.total, B_CHUNK / B_SPLIT / 256));
+  PNR_TRY(cached_tmap(&p.tm_zc, pl.zc, (size_t)pl.zc_slots * 2 * pl.nsl * A_SLICE, A_SLICE / A_SPLIT / 256));
   {
-    ProfScope ps(PROF_PHASE_A, 2.0 * mac_pre * (double)P * ns, 0.0, st);
+    ProfScope ps(PROF_FUSED_MLP, 2.0 * (mac_pre * ns + mac_post) * (double)P, 0.0, st);
     // issuer mode by latent width (see mma_elect): PNR_SOLO_MMA=0/1 forces one of them
     static const int force = [] { const char* e = getenv("PNR_SOLO_MMA"); return e ? atoi(e) : -1; }();
     const bool solo = force >= 0 ? force != 0 : L.nks_z <= 4;
-    PNR_TRY(launch_cluster(solo ? mlp_phaseA_kernel<true> : mlp_phaseA_kernel<false>, num_pairs(pl.tilesA), p, st));
-  }
-  {
-    ProfScope ps(PROF_PHASE_B, 2.0 * mac_post * (double)P, 0.0, st);
-    PNR_TRY(launch_cluster(mlp_phaseB_kernel, num_pairs(pl.tilesB), p, st));
+    PNR_TRY(launch_cluster(d, solo, pl.pairs, p, st));
   }
   return PNR_OK;
 }
 
 int tc_check(cudaStream_t st) {
   cudaError_t e = cudaStreamSynchronize(st);
-  int v = g_err_host ? *(volatile int*)g_err_host : 0;
+  DeviceState* d = nullptr;
+  int v = 0;
+  if (device_state(&d) == PNR_OK) {
+    v = *(volatile int*)d->err_host;
+    d->err_host[0] = 0;
+  }
   if (v != 0) {
-    g_err_host[0] = 0;
     set_err("tensor-core MLP pipeline: barrier wait timed out (tag %d)%s", v,
             e != cudaSuccess ? "; the kernel trapped and the CUDA context is lost" : "");
     return PNR_ERR_CUDA;
@@ -1465,8 +1439,10 @@ int tc_check(cudaStream_t st) {
 
 size_t net_tc_workspace(const pnr_scene& sc, const pnr_mlp& m, int SB, long long P) {
   if (tc_supported(m) != PNR_OK) return 256;
+  DeviceState* d = nullptr;
+  if (device_state(&d) != PNR_OK) return 256;
   Layout L = make_layout(m);
-  return make_plan(L, sc.ns, (long long)SB * P, nullptr, 0).total;
+  return make_plan(L, d->sms, sc.ns, (long long)SB * P, true, nullptr, 0).total;
 }
 
 int net_forward_tc(const pnr_scene& sc, const pnr_mlp& m, const float* xyz, const float* viewdirs, const float* rays,
@@ -1478,35 +1454,26 @@ int net_forward_tc(const pnr_scene& sc, const pnr_mlp& m, const float* xyz, cons
   for (int l = 0; l < sc.n_levels; ++l)
     PNR_UNSUPPORTED(sc.C[l] % 8 != 0 || sc.ch_off[l] % 8 != 0, "bf16 gather needs channel counts that are multiples of 8");
   PNR_CHECK_ARG(m.packed_bytes >= make_layout(m).total, "mlp.packed image too small");
+  PNR_CHECK_ARG(((uintptr_t)out & 15) == 0, "net_forward: out must be 16-byte aligned");
+  PNR_CHECK_ARG(P > 0 && P < (1LL << 31), "net_forward_tc: point count out of range");
+  DeviceState* d = nullptr;
+  PNR_TRY(device_state(&d));
   Layout L = make_layout(m);
-  Plan pl = make_plan(L, sc.ns, P, ws, ws_bytes);
+  Plan pl = make_plan(L, d->sms, sc.ns, P, true, ws, ws_bytes);
   if (pl.total > ws_bytes + 256 || !ws) {
     set_err("net_forward_tc: workspace too small (%zu < %zu)", ws_bytes, pl.total);
     return PNR_ERR_WORKSPACE;
   }
-  static const bool fused = [] {
-    const char* e = getenv("PNR_FUSED_GATHER");
-    return !(e && e[0] == '0');
-  }();
-  if (fused) {
-    GatherArgs ga{&sc, xyz, viewdirs, rays, z, K};
-    return run_phases(m, L, pl, sc.ns, P, out, 1, st, &ga);
-  }
-  long long wrows = (long long)pl.tilesA * 128;
-  {
-    // algorithmic gather bytes: 4 taps x d_latent x 2 B per (point, view) + operand row written once
-    ProfScope ps(PROF_FEATURES, 0.0, (double)P * sc.ns * (4.0 * sc.d_latent * 2 + (double)pl.nsl * 128), st);
-    point_features_bf16_kernel<<<(unsigned)ceil_div_ll(wrows, 8), 256, 0, st>>>(sc, xyz, viewdirs, rays, z, K, P, pl.ppw,
-                                                                              pl.tilesA, L.nks_z, L.nks_c, pl.zc);
-    PNR_LAUNCHED();
-  }
-  return run_phases(m, L, pl, sc.ns, P, out, 1, st);
+  GatherArgs ga{&sc, xyz, viewdirs, rays, z, K};
+  return run_fused(*d, m, L, pl, sc.ns, P, out, 1, st, &ga);
 }
 
 size_t mlp_tc_rows_workspace(const pnr_mlp& m, int SB, int NS, int P) {
   if (tc_supported(m) != PNR_OK) return 256;
+  DeviceState* d = nullptr;
+  if (device_state(&d) != PNR_OK) return 256;
   Layout L = make_layout(m);
-  return make_plan(L, NS, (long long)SB * P, nullptr, 0).total;
+  return make_plan(L, d->sms, NS, (long long)SB * P, false, nullptr, 0).total;
 }
 
 int mlp_forward_tc_rows(const pnr_mlp& m, const float* zx, int SB, int NS, int P, float* out, void* ws, size_t ws_bytes,
@@ -1515,8 +1482,11 @@ int mlp_forward_tc_rows(const pnr_mlp& m, const float* zx, int SB, int NS, int P
   PNR_UNSUPPORTED(NS > 32, "more than 32 source views per object");
   Layout L = make_layout(m);
   PNR_CHECK_ARG(m.packed_bytes >= L.total, "mlp.packed image too small");
+  PNR_CHECK_ARG(((uintptr_t)out & 15) == 0, "mlp_forward: out must be 16-byte aligned");
+  DeviceState* d = nullptr;
+  PNR_TRY(device_state(&d));
   long long pts = (long long)SB * P;
-  Plan pl = make_plan(L, NS, pts, ws, ws_bytes);
+  Plan pl = make_plan(L, d->sms, NS, pts, false, ws, ws_bytes);
   if (pl.total > ws_bytes + 256 || !ws) {
     set_err("mlp_forward_tc: workspace too small (%zu < %zu)", ws_bytes, pl.total);
     return PNR_ERR_WORKSPACE;
@@ -1525,7 +1495,7 @@ int mlp_forward_tc_rows(const pnr_mlp& m, const float* zx, int SB, int NS, int P
   rows_to_operand_kernel<<<(unsigned)ceil_div_ll(wrows, 8), 256, 0, st>>>(zx, m.d_latent, m.d_in, SB, NS, P, pl.ppw,
                                                                         pl.tilesA, L.nks_z, L.nks_c, pl.zc);
   PNR_LAUNCHED();
-  return run_phases(m, L, pl, NS, pts, out, 0, st);
+  return run_fused(*d, m, L, pl, NS, pts, out, 0, st);
 }
 
 }  // namespace pnr

@@ -95,15 +95,19 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // Slow path kept OUT OF LINE: the kernels wait at ~40 sites, and the instruction footprint of the
 // role loops matters (the L1.5 I-cache is 32 KB; code beyond it streams from an L2 that is busy with
 // the weight stream).
+// err[0] = fault tag of this device (0 = none), err[1] = timeout in ms (0 = wait for ever: debuggers,
+// compute-sanitizer, time-sliced GPUs; PNR_WAIT_TIMEOUT_MS)
 static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* err, int tag) {
   unsigned long long t0 = 0;
   for (uint32_t it = 1;; ++it) {
     if (mbar_try_wait_hint(bar, parity, 100000u)) return;
     if ((it & 15) == 0) {
       if (err && *(volatile int*)err != 0) return;
+      const unsigned long long limit = err ? (unsigned long long)(*(volatile int*)(err + 1)) * 1000000ull : 2000000000ull;
+      if (limit == 0) continue;
       unsigned long long now = globaltimer_ns();
       if (t0 == 0) t0 = now;
-      if (now - t0 > 1000000000ull) {
+      if (now - t0 > limit) {
         // *err lives in mapped pinned host memory: the tag survives the trap (which is the loud,
         // deterministic way out -- draining a half-synchronised tcgen05 pipeline is not safe)
         if (err) {
@@ -119,8 +123,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
   // try_wait itself suspends the thread for a hardware-bounded interval, so this loop does not
   // spin hot.  (Default .acquire.cta semantics on purpose: a cluster-scope acquire makes ptxas emit
   // CCTL.IVALL -- a full L1 invalidate -- after every probe, which dominated the first profile.)
-  // Wall-clock bound: 1 s without progress records `tag` in *err; once *err is set every wait in the
-  // grid gives up immediately, so a protocol bug drains the kernel in about a second.
+  // Wall-clock bound (err[1] ms, default 2 s) without progress records `tag` in *err; once *err is set every
+  // wait in the grid gives up immediately, so a protocol bug drains the kernel in about that time.
   if (mbar_try_wait(bar, parity)) return;
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity, err, tag);

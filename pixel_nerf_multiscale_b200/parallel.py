@@ -43,30 +43,43 @@ def shard_rays(rays, rank=None, world=None):
 
 
 def gather_outputs(t, total, dim=1, group=None):
-    """All-gather per-rank slices (possibly of unequal length along `dim`) back to `total` items."""
+    """All-gather per-rank slices (possibly of unequal length along `dim`) back to `total` items.
+    Collective: one ``ncclAllGather`` (``dist.all_gather_into_tensor``) of the slices padded to the longest."""
     world = dist.get_world_size(group)
+    if world == 1:
+        return t
+    if dim != 0:
+        return gather_outputs(t.transpose(0, dim).contiguous(), total, 0, group).transpose(0, dim)
     sizes = [shard_bounds(total, r, world) for r in range(world)]
     longest = max(hi - lo for lo, hi in sizes)
-    pad_shape = list(t.shape)
-    pad_shape[dim] = longest
-    buf = t.new_zeros(pad_shape)
-    buf.narrow(dim, 0, t.shape[dim]).copy_(t)
-    parts = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(parts, buf, group=group)
-    return torch.cat([p.narrow(dim, 0, hi - lo) for p, (lo, hi) in zip(parts, sizes)], dim=dim)
+    if t.shape[0] == longest and t.is_contiguous():
+        buf = t
+    else:
+        buf = t.new_zeros((longest,) + tuple(t.shape[1:]))
+        buf[: t.shape[0]].copy_(t)
+    out = t.new_empty((world * longest,) + tuple(t.shape[1:]))
+    dist.all_gather_into_tensor(out, buf, group=group)
+    if total == world * longest:
+        return out
+    return torch.cat([out[r * longest: r * longest + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], dim=0)
 
 
 def render_views(render_par, poses, width, height, focal, z_near, z_far, c=None, ray_batch_size=50000,
-                 rank=None, world=None, gather=True, group=None):
+                 rank=None, world=None, gather=True, group=None, ray_range=None, host_rays=None):
     """The frame loop of the reference's drivers (eval/gen_video.py:174-237, eval/eval.py:250-292)
     with the rays generated where they are rendered: every rank derives ITS contiguous
     range of the NV*H*W rays from (poses, focal, c) -- no (NV,H,W,8) host tensor, no scatter --
     renders it in ``ray_batch_size`` batches through ``render_par`` (``bind_parallel(...,
-    simple_output=True)``) and, with ``gather``, all ranks receive the whole frames.
+    simple_output=True)``) and, with ``gather``, all ranks receive the whole frames through ONE
+    all-gather of the packed (rgb, depth) rows.
 
     :param poses (NV,4,4) camera-to-world on the rendering device
-    :return rgb (NV,H,W,3), depth (NV,H,W); without ``gather`` this rank's flat slices
-            (n,3), (n,) and its [lo, hi) ray range
+    :param ray_range optional (g0, g1): render only rays [g0, g1) of the flattened NV*H*W rays (the
+           drivers' ``torch.split(render_rays.view(-1, 8), ray_batch_size)`` batches cross frame borders)
+    :param host_rays optional (NV*H*W, 8) CPU tensor (pinned): take the rays from the host like the
+           reference's drivers do (``util.gen_rays(...).to(device)``), copying only this rank's slice
+    :return rgb (NV,H,W,3), depth (NV,H,W); with ``ray_range`` flat (n,3), (n,); without ``gather``
+            this rank's flat slices (n,3), (n,) and its [lo, hi) ray range
     """
     from . import util
 
@@ -76,26 +89,30 @@ def render_views(render_par, poses, width, height, focal, z_near, z_far, c=None,
     if world is None:
         world = dist.get_world_size(group) if distributed else 1
     nv, per_frame = poses.shape[0], width * height
-    total = nv * per_frame
+    g0, g1 = (0, nv * per_frame) if ray_range is None else ray_range
+    total = g1 - g0
     lo, hi = shard_bounds(total, rank, world)
-    rgb_parts, depth_parts = [], []
+    lo, hi = lo + g0, hi + g0
+    dev = poses.device
+    parts = []
     if hi > lo:
-        f0, f1 = lo // per_frame, (hi - 1) // per_frame + 1   # frames this range touches
-        rays = util.gen_rays(poses[f0:f1], width, height, focal, z_near, z_far, c=c).reshape(-1, 8)
-        rays = rays[lo - f0 * per_frame: hi - f0 * per_frame]
+        if host_rays is not None:
+            rays = host_rays[lo:hi].to(dev, non_blocking=True)
+        else:
+            f0, f1 = lo // per_frame, (hi - 1) // per_frame + 1   # frames this range touches
+            rays = util.gen_rays(poses[f0:f1], width, height, focal, z_near, z_far, c=c).reshape(-1, 8)
+            rays = rays[lo - f0 * per_frame: hi - f0 * per_frame]
         for batch in torch.split(rays, ray_batch_size, dim=0):
             rgb, depth = render_par(batch[None])
-            rgb_parts.append(rgb[0])
-            depth_parts.append(depth[0])
-    dev = poses.device
-    rgb = torch.cat(rgb_parts) if rgb_parts else torch.zeros(0, 3, device=dev)
-    depth = torch.cat(depth_parts) if depth_parts else torch.zeros(0, device=dev)
+            parts.append(torch.cat((rgb[0], depth[0].unsqueeze(-1)), dim=-1))   # packed (n, 4) rows
+    out4 = (parts[0] if len(parts) == 1 else torch.cat(parts)) if parts else torch.zeros(0, 4, device=dev)
     if not gather:
-        return rgb, depth, (lo, hi)
+        return out4[:, :3], out4[:, 3], (lo, hi)
     if world > 1:
-        rgb = gather_outputs(rgb.contiguous(), total, dim=0, group=group)
-        depth = gather_outputs(depth.contiguous(), total, dim=0, group=group)
-    return rgb.reshape(nv, height, width, 3), depth.reshape(nv, height, width)
+        out4 = gather_outputs(out4.contiguous(), total, dim=0, group=group)
+    if ray_range is not None:
+        return out4[:, :3], out4[:, 3]
+    return out4[:, :3].reshape(nv, height, width, 3), out4[:, 3].reshape(nv, height, width)
 
 
 def broadcast_scene(net, src=0, group=None):

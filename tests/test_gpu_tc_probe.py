@@ -23,8 +23,8 @@ def _panels(mat, rows_per_cta):
 def _probe(mode, A, B, K):
     from pixel_nerf_multiscale_b200 import _native as N
 
-    lib = N.lib()
-    fn = lib.pnr_tc_probe
+    N.lib()
+    fn = N.probe_lib().pnr_tc_probe
     fn.restype = C.c_int
     fn.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     ncols = 256 if mode == 1 else 128

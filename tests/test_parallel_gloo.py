@@ -45,6 +45,12 @@ def _worker(rank, world, port, q):
     exp_rgb, exp_depth = fake_render(full)
     frames_ok = rgb.shape == (3, 5, 7, 3) and torch.equal(rgb, exp_rgb) and torch.equal(depth, exp_depth)
     _, _, (lo, hi) = render_views(fake_render, vposes, 7, 5, 30.0, 0.5, 3.0, gather=False)
+    # a ray batch that crosses frame borders (the drivers' torch.split batches), device-generated and host-fed
+    flat = full.reshape(-1, 8)
+    for host in (None, flat):
+        rr, dd = render_views(fake_render, vposes, 7, 5, 30.0, 0.5, 3.0, ray_batch_size=13, ray_range=(10, 81),
+                              host_rays=host)
+        frames_ok = frames_ok and torch.equal(rr, exp_rgb.reshape(-1, 3)[10:81]) and torch.equal(dd, exp_depth.reshape(-1)[10:81])
     q.put((rank, sig, mine.shape[1], torch.equal(back, rays[..., :3]) and frames_ok and (hi - lo) in (52, 53)))
     dist.destroy_process_group()
 

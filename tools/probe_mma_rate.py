@@ -3,7 +3,7 @@ import ctypes as C, sys, os
 sys.path.insert(0, os.getcwd())
 import torch
 from pixel_nerf_multiscale_b200 import _native as N
-fn = N.lib().pnr_tc_rate_probe
+N.lib(); fn = N.probe_lib().pnr_tc_rate_probe
 fn.restype = C.c_int
 fn.argtypes = [C.c_int] * 6 + [C.c_void_p] * 3
 out = torch.zeros(4, device="cuda"); err = torch.zeros(1, dtype=torch.int32, device="cuda")

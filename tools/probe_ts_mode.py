@@ -11,7 +11,7 @@ def panels(mat, rows_per_cta):
     t = mat.reshape(R // rows_per_cta, rows_per_cta, K // 8, 8).permute(0, 2, 1, 3).contiguous()
     return t.to(torch.bfloat16).reshape(-1)
 
-fn = N.lib().pnr_tc_probe
+N.lib(); fn = N.probe_lib().pnr_tc_probe
 fn.restype = C.c_int
 fn.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
 for K in (16, 32):

@@ -4,7 +4,7 @@ import ctypes as C, sys, os
 sys.path.insert(0, os.getcwd())
 import torch
 from pixel_nerf_multiscale_b200 import _native as N
-fn = N.lib().pnr_tc_probe
+N.lib(); fn = N.probe_lib().pnr_tc_probe
 fn.restype = C.c_int
 fn.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
 K = 16
