@@ -5,6 +5,8 @@
 
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 
 namespace pnr {
@@ -23,6 +25,14 @@ int64_t& launch_counter() {
   static thread_local int64_t n = 0;
   return n;
 }
+
+// NVTX ranges named after the reference's torch.autograd.profiler.record_function scopes (SURVEY.md section 5:
+// renderer_forward nerf.py:264, renderer_composite :175, model_inference models.py.backup2:165), so a timeline
+// of this library reads like one of the reference.  Free when no tool is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ---- profiling -------------------------------------------------------------------------------
 struct ProfRec {
@@ -148,6 +158,7 @@ static size_t net_chunk_workspace(const pnr_scene& sc, const pnr_mlp& m, int pre
 static int net_eval(const pnr_scene& sc, const pnr_mlp& m, int precision, const float* xyz, const float* vd,
                     const float* rays, const float* z, int K, int SB, long long P, float* out, void* ws,
                     size_t ws_bytes, cudaStream_t st) {
+  NvtxRange nvtx("model_inference");
   long long Pc = chunk_points(sc, precision, K, P);
   for (int sb = 0; sb < SB; ++sb) {
     pnr_scene os = object_scene(sc, sb);
@@ -412,13 +423,17 @@ int pnr_render_rays(const pnr_scene* scene, const pnr_mlp* coarse, const pnr_mlp
     set_err("render_rays: workspace too small (%zu < %zu)", workspace_bytes, p.total);
     return PNR_ERR_WORKSPACE;
   }
+  NvtxRange nvtx("renderer_forward");
   const int R = SB * B, Kc = cfg->n_coarse, K = cfg->n_coarse + cfg->n_fine;
   float* z_c = out->z_coarse ? out->z_coarse : p.z_c;
   float* w_c = out->weights_coarse ? out->weights_coarse : p.w_c;
   PNR_TRY(launch_sample_coarse(rays, tape->coarse_jitter, R, Kc, cfg->lindisp, z_c, st));
-  PNR_TRY(net_eval(*scene, *coarse, cfg->precision, nullptr, nullptr, rays, z_c, Kc, SB, (long long)B * Kc, p.out_c,
-                   p.net_ws, p.net_ws_bytes, st));
-  PNR_TRY(launch_composite(rays, z_c, p.out_c, R, Kc, cfg->white_bkgd, w_c, out->rgb_coarse, out->depth_coarse, st));
+  {
+    NvtxRange nc("renderer_composite");
+    PNR_TRY(net_eval(*scene, *coarse, cfg->precision, nullptr, nullptr, rays, z_c, Kc, SB, (long long)B * Kc, p.out_c,
+                     p.net_ws, p.net_ws_bytes, st));
+    PNR_TRY(launch_composite(rays, z_c, p.out_c, R, Kc, cfg->white_bkgd, w_c, out->rgb_coarse, out->depth_coarse, st));
+  }
   if (cfg->n_fine > 0) {
     PNR_CHECK_ARG(out->rgb_fine && out->depth_fine, "render_rays: fine outputs missing");
     int n_imp = cfg->n_fine - cfg->n_fine_depth;
@@ -429,6 +444,7 @@ int pnr_render_rays(const pnr_scene* scene, const pnr_mlp* coarse, const pnr_mlp
     PNR_TRY(launch_sample_fine_sorted(rays, z_c, w_c, out->depth_coarse, tape->fine_u, tape->fine_jitter,
                                       tape->depth_normal, R, Kc, cfg->n_fine, cfg->n_fine_depth, cfg->depth_std,
                                       cfg->lindisp, z_f, st));
+    NvtxRange nc("renderer_composite");
     PNR_TRY(net_eval(*scene, fine ? *fine : *coarse, cfg->precision, nullptr, nullptr, rays, z_f, K, SB,
                      (long long)B * K, p.out_f, p.net_ws, p.net_ws_bytes, st));
     PNR_TRY(launch_composite(rays, z_f, p.out_f, R, K, cfg->white_bkgd, w_f, out->rgb_fine, out->depth_fine, st));

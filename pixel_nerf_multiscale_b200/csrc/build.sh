@@ -13,7 +13,7 @@ for f in api features mlp_f32 rays mlp_tc tc_probe; do
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$BUILD"/{api,features,mlp_f32,rays,mlp_tc}.o -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$BUILD"/{api,features,mlp_f32,rays,mlp_tc}.o -lcudart -ldl
 # hardware probes (tests/test_gpu_tc_probe.py, tools/probe_*.py): their own library, not part of the product ABI
 OUTDIR="$(cd "$(dirname "$OUT")" && pwd)"
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUTDIR/libpixelnerf_b200_probe.so" "$BUILD/tc_probe.o" \

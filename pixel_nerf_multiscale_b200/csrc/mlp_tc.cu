@@ -95,7 +95,7 @@ struct Params {
   unsigned long long* stats;           // optional [pairs][16] cycle counters (debug)
   // in-kernel gather (warps 2-3 of phase A produce the operand image one tile ahead of the MMAs)
   int fused_gather;                    // 0: zc was written by rows_to_operand_kernel (pnr_mlp_forward)
-  int zc_ring;                         // > 0 (fused gather): zc holds zc_ring tiles per cluster pair, reused round-robin,
+  int zc_ring;                         // > 0 (fused gather): zc holds zc_ring (2) tiles per cluster pair, reused round-robin,
                                        // so the image stays in L2 and is never written back to DRAM; 0: one slot per tile
   const float *xyz, *viewdirs, *rays, *zsamp;
   int K;
@@ -931,7 +931,8 @@ __device__ __noinline__ void head_tile(const Params& p, Ctx cx, const Epi e, uin
         if (p.apply_head) s = (o < 3) ? 1.f / (1.f + __expf(-s)) : fmaxf(s, 0.f);
         o4[o] = s;
       }
-      reinterpret_cast<float4*>(p.out)[gp_row] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+      // streaming store: consumed once by the compositing kernel, must not displace the L2-resident rings
+      __stcs(reinterpret_cast<float4*>(p.out) + gp_row, make_float4(o4[0], o4[1], o4[2], o4[3]));
     }
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");  // s_wout / s_part (= S_x) may be overwritten from here on
@@ -1075,18 +1076,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
         bool valid;
         long long gp = tileA_point(tile, (int)cx.rank, row, p.ns, p.ppw, v, valid);
         valid = valid && gp < p.P;
-        // slot (git % 3) of this pair: written while the producer still reads slot (git-1) % 3; slot git % 3 was
-        // last read for tile git-3, whose loads completed before the producer took tile git-1 (ZC_TAKEN)
+        // 2-deep ring per pair: slot git % 2 last held tile git-2.  The producer "takes" tile git-1 only after it has
+        // issued every load of tile git-2, and the ring slots those loads used have been recycled since (so they
+        // have landed): once ZC_TAKEN(git-1) completed the slot is free.  The gather therefore runs exactly one
+        // tile ahead of the MMAs, and the image (2 x 2 x nsl x 8 KB per pair) stays resident in L2.
+        if (git >= 1) twait(cx, 2, cx.bar(ZC_TAKEN), (git - 1) & 1, 204);
         const size_t zslot = p.zc_ring ? (size_t)pair * p.zc_ring + git % p.zc_ring : (size_t)tile;
         uint8_t* base = const_cast<uint8_t*>(p.zc) + ((zslot * 2 + cx.rank) * nsl) * A_SLICE + (size_t)row * 16;
         gather_row_to_zc(p.sc, p.xyz, p.viewdirs, p.rays, p.zsamp, p.K, gp, v, valid, p.nks_z, p.nks_c, base);
-        // generic-proxy global writes -> visible to the async proxy (TMA) of this SM before the signal
+        // generic-proxy global writes -> visible to the async proxy (TMA) of this SM before the signal.  (The wait
+        // above also keeps ZC_READY from completing twice before the producer looks.)
         __threadfence();
         asm volatile("fence.proxy.async;" ::: "memory");
-        // Signal only after the producer has consumed the previous tile's signal: a 1-phase-deep
-        // mbarrier must never complete twice before its waiter looks (and this also keeps the
-        // gather at most ~one tile ahead, so the image is still in L2 when TMA reads it).
-        if (git >= 1) twait(cx, 2, cx.bar(ZC_TAKEN), (git - 1) & 1, 204);
         __syncwarp();
         if (lane == 0) mbar_arrive(cx.bar(ZC_READY));
       }
@@ -1243,6 +1244,7 @@ static int take_fault(DeviceState& d, const char* when) {
   return PNR_ERR_CUDA;
 }
 
+constexpr int ZC_RING = 2;  // operand-image tiles per pair (see the gather warps)
 struct Plan {
   int ppw, ptile, tilesA, nA, nsl, pairs, zc_slots;
   uint8_t* zc;
@@ -1257,7 +1259,7 @@ static int pairs_for(int sms, int tiles) {
   return tiles < pairs ? (tiles > 0 ? tiles : 1) : pairs;
 }
 
-// `ring`: the operand image is produced inside the kernel (gather warps) and needs only 3 slots per pair
+// `ring`: the operand image is produced inside the kernel (gather warps) and needs only ZC_RING slots per pair
 static Plan make_plan(const Layout& L, int sms, int ns, long long P, bool ring, void* ws, size_t ws_bytes) {
   Plan pl;
   pl.ppw = 64 / ns;
@@ -1266,7 +1268,7 @@ static Plan make_plan(const Layout& L, int sms, int ns, long long P, bool ring, 
   pl.tilesA = (int)ceil_div_ll(P, pl.ptile);
   pl.nsl = L.nks_z + L.nks_c;
   pl.pairs = pairs_for(sms, pl.tilesA);
-  pl.zc_slots = (ring && pl.tilesA > 3 * pl.pairs) ? 3 * pl.pairs : pl.tilesA;
+  pl.zc_slots = (ring && pl.tilesA > ZC_RING * pl.pairs) ? ZC_RING * pl.pairs : pl.tilesA;
   Arena a(ws, ws_bytes);
   pl.zc = a.take<uint8_t>((size_t)pl.zc_slots * 2 * pl.nsl * A_SLICE);
   pl.stage = a.take<float>((size_t)pl.pairs * 2 * ROWS * DH);
@@ -1395,7 +1397,7 @@ static int run_fused(DeviceState& d, const pnr_mlp& m, const Layout& L, const Pl
   p.apply_head = head;
   if (ga) {
     p.fused_gather = 1;
-    p.zc_ring = (pl.zc_slots < pl.tilesA) ? 3 : 0;  // 3-deep ring per pair unless one slot per tile is smaller
+    p.zc_ring = (pl.zc_slots < pl.tilesA) ? ZC_RING : 0;  // ring per pair unless one slot per tile is smaller
     p.sc = *ga->sc;
     p.xyz = ga->xyz;
     p.viewdirs = ga->viewdirs;

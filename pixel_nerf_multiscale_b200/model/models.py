@@ -83,6 +83,11 @@ class PixelNeRFNet(torch.nn.Module):
         :param poses (NS,4,4) or (SB,NS,4,4) camera-to-world
         :param focal () | (2) | (N) | (N,2)   :param c None | () | (2) | (N) | (N,2)
         """
+        # the fork's eval/gen_video.py:204 passes the source images on the CPU while the model lives on the
+        # GPU (upstream moves them first); accept that instead of failing inside the first convolution
+        dev = self.poses.device
+        images, poses, focal = images.to(dev), poses.to(dev), focal.to(dev)
+        c = c if c is None else c.to(dev)
         self.num_objs = images.size(0)
         if images.dim() == 5:
             assert poses.dim() == 4
@@ -153,6 +158,13 @@ class PixelNeRFNet(torch.nn.Module):
         maps = self.encoder.level_maps()
         if len(maps) == 0 or maps[0] is None:
             raise RuntimeError("PixelNeRFNet.forward called before encode()")
+        # the native gather implements grid_sample(bilinear, border, align_corners=True) only
+        # (src/model/encoder.py:182-188 with the shipped confs); other conf values would render differently
+        interp = getattr(self.encoder, "index_interp", "bilinear")
+        padding = getattr(self.encoder, "index_padding", "border")
+        if interp != "bilinear" or padding != "border":
+            raise NotImplementedError("encoder.index_interp=%r / index_padding=%r are not supported by the native "
+                                      "gather (only bilinear / border)" % (interp, padding))
         device = self.poses.device
         if device.type != "cuda":
             raise RuntimeError("pixelnerf_b200: the rendering path needs the model on a CUDA device (no CPU path)")
@@ -230,7 +242,8 @@ class PixelNeRFNet(torch.nn.Module):
         m, _keep_m = self.native_mlp(coarse)
         out = torch.empty(SB, B, self.d_out, dtype=torch.float32, device=xyz.device)
         lib = N.lib()
-        with torch.cuda.device(xyz.device):
+        # same scope name as models.py.backup2:165
+        with torch.autograd.profiler.record_function("model_inference"), torch.cuda.device(xyz.device):
             nbytes = lib.pnr_net_forward_workspace(sc, m, SB, B, prec)
             ws = self.workspace(nbytes, xyz.device)
             N.check(lib.pnr_net_forward(sc, m, N.ptr(xyz), N.ptr(viewdirs), SB, B, prec, N.ptr(out), N.ptr(ws),

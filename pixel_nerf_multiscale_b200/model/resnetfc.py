@@ -77,11 +77,29 @@ class ResnetFC(nn.Module):
         # the native descriptors (ctypes structs with device pointers) are a cache: never copied/pickled
         state = self.__dict__.copy()
         state["_native_cache"] = {}
+        state["_param_list"] = None
         return state
 
     # ---- native operand bookkeeping -------------------------------------------------------
     def _fingerprint(self):
-        return tuple((p.data_ptr(), p._version, str(p.device)) for p in self.parameters())
+        """Cheap identity of the current parameter values: storage pointer + in-place version counter of
+        every parameter (torch bumps ``_version`` on copy_/load_state_dict/optimizer steps; ``.to()`` /
+        ``_apply`` replace the storages).  The parameter list itself is cached (it only changes when a
+        submodule is replaced, which ``_apply`` / ``load_state_dict`` below invalidate)."""
+        ps = self.__dict__.get("_param_list")
+        if ps is None:
+            ps = self.__dict__["_param_list"] = list(self.parameters())
+        return tuple([(p.data_ptr(), p._version) for p in ps])
+
+    def _apply(self, fn, *a, **kw):
+        self.__dict__["_param_list"] = None
+        self._native_cache = {}
+        return super()._apply(fn, *a, **kw)
+
+    def load_state_dict(self, *a, **kw):
+        self.__dict__["_param_list"] = None
+        self._native_cache = {}
+        return super().load_state_dict(*a, **kw)
 
     def native(self, precision):
         """ctypes Mlp descriptor for the current parameters (re-packed lazily after any
@@ -148,7 +166,8 @@ class ResnetFC(nn.Module):
         m, keep = self.native(precision)
         out = torch.empty(sb * p, self.d_out, dtype=torch.float32, device=zx.device)
         lib = N.lib()
-        with torch.cuda.device(zx.device):
+        # same scope name as resnetfc.py:180
+        with torch.autograd.profiler.record_function("resnetfc_infer"), torch.cuda.device(zx.device):
             nbytes = lib.pnr_mlp_forward_workspace(m, sb, ns, p, precision)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=zx.device)
             N.check(lib.pnr_mlp_forward(m, N.ptr(rows), sb, ns, p, precision, N.ptr(out), N.ptr(ws), nbytes,

@@ -208,12 +208,17 @@ class MultiDeviceRenderer(torch.nn.Module):
         n = rays.shape[1]
         primary = self.gpus[0]
         parts = []
+        renderer = self.module.renderer
+        tape, renderer.rng_tape = renderer.rng_tape, None   # a pre-drawn tape covers the whole batch: split it per shard
         for i, dev in enumerate(self.gpus):
             lo, hi = shard_bounds(n, i, len(self.gpus))
             if hi == lo:
                 continue
             with torch.cuda.device(dev):
                 wrapper = self._replica(dev)
+                if tape is not None:
+                    assert rays.shape[0] == 1, "rng_tape with several devices needs SB == 1 (rows are ray-major)"
+                    renderer.rng_tape = {k: v[lo:hi] for k, v in tape.items()}
                 parts.append(wrapper(rays[:, lo:hi].to(dev, non_blocking=True), want_weights=want_weights))
         if len(parts) == 0:
             return self.module(rays, want_weights=want_weights)

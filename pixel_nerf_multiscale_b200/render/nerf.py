@@ -85,9 +85,22 @@ class NeRFRenderer(torch.nn.Module):
         """Reference order: coarse jitter; then (after the coarse pass) u, jitter, normal."""
         tape = self.rng_tape
         self.rng_tape = None
-        kc, kf, kd = self.n_coarse, self.n_fine, self.n_fine_depth
+        kc, kf, kd = int(self.n_coarse), int(self.n_fine), int(self.n_fine_depth)
         if tape is not None:
-            return tape
+            # a supplied tape is materialised as contiguous fp32 on the rays' device (the locals keep the
+            # copies alive across the launch) and must cover every ray: the kernels index it by ray
+            want = {"coarse": (B, kc)}
+            if self.using_fine and kf - kd > 0:
+                want["u"] = want["jitter"] = (B, kf - kd)
+            if self.using_fine and kd > 0:
+                want["normal"] = (B, kd)
+            out = {}
+            for name, shape in want.items():
+                t = tape.get(name)
+                assert t is not None, "rng_tape is missing %r" % name
+                assert tuple(t.shape) == shape, "rng_tape[%r] has shape %s, expected %s" % (name, tuple(t.shape), shape)
+                out[name] = t.to(device=device, dtype=torch.float32).contiguous()
+            return out
 
         t = {}
         t["coarse"] = torch.rand(B, kc, dtype=torch.float32, device=device)
@@ -132,7 +145,7 @@ class NeRFRenderer(torch.nn.Module):
         g = lambda lvl, k: N.ptr(res.get(lvl, {}).get(k))
         out = N.RenderOut(g("coarse", "rgb"), g("coarse", "depth"), g("coarse", "weights"), g("fine", "rgb"),
                           g("fine", "depth"), g("fine", "weights"), g("coarse", "z"), g("fine", "z"))
-        ctape = N.RngTape(N.ptr(tape["coarse"].contiguous()), N.ptr(tape.get("u")), N.ptr(tape.get("jitter")),
+        ctape = N.RngTape(N.ptr(tape["coarse"]), N.ptr(tape.get("u")), N.ptr(tape.get("jitter")),
                           N.ptr(tape.get("normal")))
         lib = N.lib()
         with torch.cuda.device(device):
@@ -180,7 +193,7 @@ class NeRFRenderer(torch.nn.Module):
 
         with torch.cuda.device(device):
             z_c = torch.empty(R, kc, **f32)
-            N.check(lib.pnr_sample_coarse(N.ptr(flat), N.ptr(tape["coarse"].contiguous()), R, kc,
+            N.check(lib.pnr_sample_coarse(N.ptr(flat), N.ptr(tape["coarse"]), R, kc,
                                           int(bool(self.lindisp)), N.ptr(z_c), N.stream_ptr(device)),
                     "pnr_sample_coarse")
             w_c, rgb_c, d_c = composite(z_c, self._eval_model(model, flat, z_c, True, sb), kc)
@@ -218,10 +231,11 @@ class NeRFRenderer(torch.nn.Module):
         if not rays.is_cuda:
             raise RuntimeError("pixelnerf_b200: NeRFRenderer needs CUDA rays (there is no CPU path)")
         sb = rays.shape[0]
-        if isinstance(model, PixelNeRFNet):
-            res = self._render_fused(model, rays, want_weights, taps)
-        else:
-            res = self._render_generic(model, rays, want_weights, taps)
+        with torch.autograd.profiler.record_function("renderer_forward"):   # same scope name as nerf.py:264
+            if isinstance(model, PixelNeRFNet):
+                res = self._render_fused(model, rays, want_weights, taps)
+            else:
+                res = self._render_generic(model, rays, want_weights, taps)
         out = RenderOutput()
         for lvl, d in res.items():
             o = RenderOutput()

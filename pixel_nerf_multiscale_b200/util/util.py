@@ -1,8 +1,12 @@
 """
 Host-side helpers the ray-rendering path and its callers need (the reference keeps them in
-src/util/util.py).  Only what the path touches is provided: ray generation
-(util.py:118-148,243-281), spherical poses (:314-328), repeat_interleave (:58-65),
-combine_interleaved (:466-476) and psnr (:479-486).
+src/util/util.py).  Only what the path and its drivers (eval/gen_video.py, eval/eval.py,
+eval/eval_real.py, eval/eval_approx.py) touch is provided: ray generation (util.py:118-148,243-281),
+spherical poses (:314-328), repeat_interleave (:58-65), combine_interleaved (:466-476), psnr (:479-486),
+get_cuda (:198-207), quat_to_rot / rot_to_quat (:489-533), the Blender coordinate flips (:151-176),
+cmap (:13-30), batched_index_select_nd (:33-55), get_image_to_tensor_balanced / get_mask_to_tensor
+(:68-86), get_module (:536-543) -- plus the device-side output tail (finalize_frames, frame_metrics,
+normalize_depth).
 """
 import math
 
@@ -92,6 +96,86 @@ def pose_spherical(theta, phi, radius):
 def psnr(pred, target):
     mse = ((pred - target) ** 2).mean()
     return -10 * math.log10(mse)
+
+
+def get_cuda(gpu_id):
+    """torch.device of GPU `gpu_id`, or the CPU device when CUDA is unavailable (the rendering path itself
+    then raises: there is no CPU implementation)."""
+    return torch.device("cuda:%d" % gpu_id) if torch.cuda.is_available() else torch.device("cpu")
+
+
+def get_module(net):
+    """net.module for DataParallel-style wrappers (incl. parallel.MultiDeviceRenderer), else net."""
+    return net.module if hasattr(net, "module") and isinstance(net.module, torch.nn.Module) else net
+
+
+def quat_to_rot(q):
+    """(B,4) quaternions (w,x,y,z; normalised here) -> (B,3,3) rotation matrices."""
+    q = torch.nn.functional.normalize(q, dim=1)
+    w, x, y, z = q.unbind(dim=1)
+    rows = (1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+            2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+            2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y))
+    return torch.stack(rows, dim=1).reshape(-1, 3, 3)
+
+
+def rot_to_quat(R):
+    """(B,3,3) rotations -> (B,4) quaternions (w,x,y,z), the trace > -1 branch the reference uses."""
+    w = torch.sqrt(1.0 + R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2]) / 2
+    return torch.stack((w, (R[:, 2, 1] - R[:, 1, 2]) / (4 * w), (R[:, 0, 2] - R[:, 2, 0]) / (4 * w),
+                        (R[:, 1, 0] - R[:, 0, 1]) / (4 * w)), dim=1)
+
+
+def coord_from_blender(dtype=torch.float32, device="cpu"):
+    """Blender (x right, y in, z up) -> standard (x right, y up, z out) transform, (4,4)."""
+    return torch.tensor([[1, 0, 0, 0], [0, 0, 1, 0], [0, -1, 0, 0], [0, 0, 0, 1]], dtype=dtype, device=device)
+
+
+def coord_to_blender(dtype=torch.float32, device="cpu"):
+    """Standard -> Blender coordinate transform, (4,4)."""
+    return torch.tensor([[1, 0, 0, 0], [0, 0, -1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=dtype, device=device)
+
+
+def batched_index_select_nd(t, inds):
+    """t (B, N, ...), inds (B, M) -> (B, M, ...): per-batch row selection along dim 1."""
+    idx = inds.reshape(inds.shape[0], inds.shape[1], *([1] * (t.dim() - 2))).expand(-1, -1, *t.shape[2:])
+    return t.gather(1, idx)
+
+
+def get_image_to_tensor_balanced(image_size=0):
+    """PIL image -> (3,H,W) tensor in [0,1] (the fork dropped upstream's [-1,1] normalisation)."""
+    from torchvision import transforms
+
+    ops = [transforms.Resize(image_size)] if image_size > 0 else []
+    return transforms.Compose(ops + [transforms.ToTensor()])
+
+
+def get_mask_to_tensor():
+    from torchvision import transforms
+
+    return transforms.Compose([transforms.ToTensor(), transforms.Normalize((0.0,), (1.0,))])
+
+
+def image_float_to_uint8(img):
+    """float image -> uint8 after min/max stretching (numpy)."""
+    import numpy as np
+
+    lo, hi = float(np.min(img)), float(np.max(img))
+    if hi - lo < 1e-10:
+        hi += 1e-10
+    return ((img - lo) / (hi - lo) * 255.0).astype(np.uint8)
+
+
+def cmap(img, color_map=None):
+    """'HOT' colour map of a float image (eval.py --write_depth)."""
+    import cv2
+
+    return cv2.applyColorMap(image_float_to_uint8(img), cv2.COLORMAP_HOT if color_map is None else color_map)
+
+
+def normalize_depth(depth, z_near, z_far):
+    """(depth - z_near) / (z_far - z_near), the depth image eval/eval.py:284 writes -- on the depth's device."""
+    return (depth - float(z_near)) / (float(z_far) - float(z_near))
 
 
 def frame_metrics(rgb, target, data_range=1.0, win_size=7):

@@ -116,6 +116,8 @@ VARIANTS = {
     "dtu_ns3": {"default": {}},
     "ms_ns3_sb2": {"default": {}},
     "sv3_ns1": {"default": {}},
+    "dtu_ns3_s6": {"default": {}},
+    "ms_ns2_s6": {"default": {}},
 }
 
 if __name__ == "__main__":

@@ -81,3 +81,34 @@ def make_renderer(conf, kw, eval_batch_size=50000):
         if k in kw:
             rconf.put(k, kw[k])
     return pk.NeRFRenderer.from_conf(rconf, lindisp=kw.get("lindisp", False), eval_batch_size=eval_batch_size)
+
+
+# ---- synthetic on-disk datasets (tests of the data adapters and of the reference's drivers) -------------------
+def write_srn_fixture(root, name="cars", stage="test", n_obj=2, n_views=4, size=32, focal=40.0, radius=1.3, seed=0):
+    """SRN-format folder ``<root>/<name>_<stage>/obj_k/{intrinsics.txt, rgb/*.png, pose/*.txt}`` with
+    seeded random images and spherical poses.  Returns the list of expected items."""
+    import cv2
+    import numpy as np
+
+    import pixel_nerf_multiscale_b200 as pk
+
+    g = np.random.RandomState(seed)
+    flip = np.diag([1.0, -1.0, -1.0, 1.0]).astype(np.float32)
+    base = os.path.join(root, "%s_%s" % (name, stage))
+    expect = []
+    for k in range(n_obj):
+        d = os.path.join(base, "obj_%02d" % k)
+        os.makedirs(os.path.join(d, "rgb"), exist_ok=True)
+        os.makedirs(os.path.join(d, "pose"), exist_ok=True)
+        with open(os.path.join(d, "intrinsics.txt"), "w") as f:
+            f.write("%f %f %f 0.\n0. 0. 0.\n1.\n%d %d\n" % (focal, size / 2.0, size / 2.0, size, size))
+        imgs, poses = [], []
+        for v in range(n_views):
+            img = g.randint(0, 255, size=(size, size, 3)).astype(np.uint8)  # never pure white: all foreground
+            cv2.imwrite(os.path.join(d, "rgb", "%06d.png" % v), img[..., ::-1])
+            pose = pk.util.pose_spherical(40.0 * v + 17.0 * k, -15.0, radius).numpy()
+            np.savetxt(os.path.join(d, "pose", "%06d.txt" % v), (pose @ flip).reshape(1, 16))
+            imgs.append(img)
+            poses.append(pose)
+        expect.append(dict(path=d, images=np.stack(imgs), poses=np.stack(poses), focal=focal, c=(size / 2.0, size / 2.0)))
+    return expect

@@ -8,10 +8,17 @@ MLPs, so sigma scales by exactly that factor while everything upstream of the he
 
     python tests/sigma_sweep.py [--workloads c2,c3,c4] [--gains 1,3,6,12] [--rays 8192] [--precision bf16]
 
-prints one JSON line per (workload, gain): sigma statistics, max-abs rgb / depth error of the coarse
-pass (identical sample positions: pure arithmetic error) and of the fine pass, the share of rays whose
-importance samples landed in a different coarse bin, and the PSNR of both renderers against a common
-pseudo ground truth (the oracle's render with other random draws) -- north_star: |dPSNR| <= 0.05 dB.
+prints one JSON line per (workload, gain): sigma statistics; max-abs rgb / depth error of
+  * the coarse pass (identical sample positions: pure arithmetic error),
+  * the fine pass AT IDENTICAL SAMPLE POSITIONS (the oracle composites the product's own fine samples:
+    again pure arithmetic error -- this and the coarse figure are what the <= 1e-2 bar is asserted on),
+  * the fine pass end to end, where a bf16-perturbed coarse weight can move an importance sample into a
+    neighbouring bin of the inverse-CDF search (the search itself is bit-exact given the CDF): both
+    renders are then valid draws of the same Monte-Carlo estimator with different sample placement, so
+    the end-to-end max is reported (with p99.9 and the share of rays that had a flip), split into
+    flipped / unflipped rays;
+and the PSNR of both renderers against a common ground truth (the oracle's fine render + N(0, 0.05) noise,
+~26 dB like a trained pixelNeRF on DTU/SRN) -- north_star: |dPSNR| <= 0.05 dB.
 Used by tests/test_gpu_fullsize.py; the committed table is profiles/r02_sigma_sweep.jsonl.
 """
 import argparse
@@ -90,8 +97,9 @@ def compare(workload, gain, n_rays, precision="bf16", seed=5, device="cuda:0", f
 
         N.check(N.lib().pnr_tc_check(N.stream_ptr(dev)), "pnr_tc_check")
         ref = po.render(gscene, rays[None], tape=Replay(tape), eval_batch_size=200000, **kw)
-        other = po.render(gscene, rays[None], tape=Replay(make_tape(n, seed + 1000, dev, kw["n_coarse"], kw["n_fine"],
-                                                                    kw["n_fine_depth"])), eval_batch_size=200000, **kw)
+        # the oracle on the PRODUCT's fine samples: same positions, fp32 arithmetic
+        _w, rgb_same, depth_same, _o = po.composite(gscene, rays, ours.fine.z[0].contiguous(), False, 1, kw["white_bkgd"],
+                                                   eval_batch_size=200000)
     torch.cuda.synchronize(dev)
     sig = ref["fine"]["out"][..., 3]
     res = {"workload": workload, "gain": gain, "rays": n, "precision": precision,
@@ -105,13 +113,25 @@ def compare(workload, gain, n_rays, precision="bf16", seed=5, device="cuda:0", f
         res[lvl + "_depth_max"] = e_d.max().item()
         res[lvl + "_rgb_p999"] = e_rgb.flatten().kthvalue(max(1, int(e_rgb.numel() * 0.999)))[0].item()
         res[lvl + "_depth_p999"] = e_d.flatten().kthvalue(max(1, int(e_d.numel() * 0.999)))[0].item()
+    res["fine_same_samples_rgb_max"] = (ours.fine.rgb[0] - rgb_same).abs().max().item()
+    res["fine_same_samples_depth_max"] = (ours.fine.depth[0] - depth_same).abs().max().item()
     res["coarse_z_bit_equal"] = bool(torch.equal(ours.coarse.z[0], ref["coarse"]["z"]))
-    dz = (ours.fine.z[0] - ref["fine"]["z"]).abs()
-    step = (wl["z_far"] - wl["z_near"]) / kw["n_coarse"]
-    res["bin_flip_rays"] = (dz.max(dim=-1)[0] > 0.5 * step).float().mean().item()
+    # a ray "flipped" when any of its importance samples fell into a different bin: the inverse-CDF search
+    # (bit-exact given a CDF) applied to the product's and to the oracle's coarse weights with the same u
+    ind_ours = po.fine_indices(po.fine_cdf(ours.coarse.weights[0]), tape["u"])
+    ind_ref = po.fine_indices(po.fine_cdf(ref["coarse"]["weights"]), tape["u"])
+    flipped = (ind_ours != ind_ref).any(dim=-1)
+    res["bin_flip_rays"] = flipped.float().mean().item()
+    e_rgb = (ours.fine.rgb[0] - ref["fine"]["rgb"]).abs().max(dim=-1)[0]
+    e_d = (ours.fine.depth[0] - ref["fine"]["depth"]).abs()
+    keep = ~flipped
+    res["fine_unflipped_rgb_max"] = e_rgb[keep].max().item() if keep.any() else 0.0
+    res["fine_unflipped_depth_max"] = e_d[keep].max().item() if keep.any() else 0.0
     res["psnr_ours_vs_ref"] = psnr(ours.fine.rgb[0], ref["fine"]["rgb"])
-    res["psnr_ours_vs_gt"] = psnr(ours.fine.rgb[0], other["fine"]["rgb"])
-    res["psnr_ref_vs_gt"] = psnr(ref["fine"]["rgb"], other["fine"]["rgb"])
+    g = torch.Generator().manual_seed(99)
+    gt = (ref["fine"]["rgb"].cpu() + 0.05 * torch.randn(ref["fine"]["rgb"].shape, generator=g)).clamp(0, 1).to(dev)
+    res["psnr_ours_vs_gt"] = psnr(ours.fine.rgb[0].clamp(0, 1), gt)
+    res["psnr_ref_vs_gt"] = psnr(ref["fine"]["rgb"].clamp(0, 1), gt)
     res["dpsnr"] = res["psnr_ours_vs_gt"] - res["psnr_ref_vs_gt"]
     del gscene, net
     torch.cuda.empty_cache()

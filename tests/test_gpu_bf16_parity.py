@@ -14,7 +14,7 @@ from helpers import (N_POINTS, RENDER_SEED, build_product, load_golden, make_ren
                      sample_points)
 
 pytestmark = pytest.mark.gpu
-CASES = ["ss_ns1", "ms_ns2", "dtu_ns3", "ms_ns3_sb2", "sv3_ns1"]
+CASES = ["ss_ns1", "ms_ns2", "dtu_ns3", "ms_ns3_sb2", "sv3_ns1", "dtu_ns3_s6", "ms_ns2_s6"]
 
 
 def _tc_check():
@@ -102,20 +102,43 @@ def test_render_bf16_vs_golden(name, variant):
     res = renderer(net, rays, want_weights=True, taps=True)
     _tc_check()
     last = "fine" if "fine_rgb" in gold else "coarse"
-    for lvl in ("coarse", "fine"):
-        if lvl + "_rgb" not in gold:
-            continue
-        e_rgb = maxabs(res[lvl].rgb.cpu(), gold[lvl + "_rgb"])
-        e_d = maxabs(res[lvl].depth.cpu(), gold[lvl + "_depth"])
-        print("%s/%s %s: rgb %.3e depth %.3e" % (name, variant, lvl, e_rgb, e_d))
-        assert e_rgb < 1e-2 and e_d < 1e-2
-    if "z_fine" in gold:
-        # coarse->fine divergence: a bf16-perturbed coarse weight can move an importance sample
-        # into a neighbouring bin (the CDF / search / compositing themselves stay fp32)
-        dz = (res.fine.z.reshape(gold["z_fine"].shape).cpu() - gold["z_fine"]).abs()
-        step = (case["z_far"] - case["z_near"]) / kw["n_coarse"]
-        flipped = (dz.max(dim=-1)[0] > 0.5 * step).float().mean().item()
-        print("rays with an importance sample in a different bin: %.1f%%" % (100 * flipped))
+    flat = rays.reshape(-1, 8)
+    # (1) coarse pass: identical sample positions -> the pure arithmetic error of the bf16 path.  Strict bar.
+    e_rgb = maxabs(res.coarse.rgb.cpu(), gold["coarse_rgb"])
+    e_d = maxabs(res.coarse.depth.cpu(), gold["coarse_depth"])
+    print("%s/%s coarse: rgb %.3e depth %.3e" % (name, variant, e_rgb, e_d))
+    assert e_rgb < 1e-2 and e_d < 1e-2
+    if "fine_rgb" in gold:
+        K = res.fine.z.shape[-1]
+        # (2) fine pass at IDENTICAL sample positions (the fp32 oracle composites the product's own samples):
+        #     again pure arithmetic error.  Strict bar, every ray.
+        with torch.no_grad():
+            _w, rgb_same, d_same, _o = po.composite(scene, flat, res.fine.z.reshape(-1, K).contiguous(), False, case["sb"],
+                                                    kw["white_bkgd"])
+        e_rgb_s, e_d_s = maxabs(res.fine.rgb.reshape(-1, 3), rgb_same), maxabs(res.fine.depth.reshape(-1), d_same)
+        print("%s/%s fine, same samples: rgb %.3e depth %.3e" % (name, variant, e_rgb_s, e_d_s))
+        assert e_rgb_s < 1e-2 and e_d_s < 1e-2
+        # (3) end to end against the reference's golden: a bf16-perturbed coarse weight can move an importance
+        #     sample into a neighbouring bin (the CDF / search / sort / compositing themselves stay fp32 and the
+        #     search is bit-exact given the CDF).  Rays without such a flip must meet the bar; rays with one are
+        #     a different, equally valid draw of the estimator: reported, and bounded loosely.
+        e_rgb_r = (res.fine.rgb.reshape(-1, 3).cpu() - gold["fine_rgb"].reshape(-1, 3)).abs().max(dim=-1)[0]
+        e_d_r = (res.fine.depth.reshape(-1).cpu() - gold["fine_depth"].reshape(-1)).abs()
+        flipped = torch.zeros_like(e_d_r, dtype=torch.bool)
+        if tape.u is not None:
+            kc = kw["n_coarse"]
+            ind_o = po.fine_indices(po.fine_cdf(res.coarse.weights.reshape(-1, kc).cpu()), tape.u)
+            ind_g = po.fine_indices(po.fine_cdf(gold["coarse_weights"].reshape(-1, kc)), tape.u)
+            flipped = (ind_o != ind_g).any(dim=-1)
+        keep = ~flipped
+        print("%s/%s fine vs golden: unflipped rays rgb %.3e depth %.3e | %d/%d rays with a flipped importance sample: "
+              "rgb %.3e depth %.3e" % (name, variant, e_rgb_r[keep].max().item() if keep.any() else -1.0,
+                                      e_d_r[keep].max().item() if keep.any() else -1.0, int(flipped.sum()),
+                                      flipped.numel(), e_rgb_r[flipped].max().item() if flipped.any() else 0.0,
+                                      e_d_r[flipped].max().item() if flipped.any() else 0.0))
+        assert keep.any(), "every ray had a flipped importance sample"
+        assert e_rgb_r[keep].max().item() < 1e-2 and e_d_r[keep].max().item() < 1e-2
+        assert e_rgb_r.max().item() < 5e-2 and e_d_r.max().item() < 1e-1
     mse = ((res[last].rgb.cpu() - gold[last + "_rgb"]) ** 2).mean().item()
     psnr = -10 * math.log10(max(mse, 1e-20))
     print("PSNR(bf16 vs reference) = %.1f dB" % psnr)

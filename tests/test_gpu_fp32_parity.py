@@ -14,7 +14,7 @@ from helpers import (N_POINTS, RENDER_SEED, build_product, load_golden, make_ren
                      sample_points)
 
 pytestmark = pytest.mark.gpu
-CASES = ["ss_ns1", "ms_ns2", "dtu_ns3", "ms_ns3_sb2", "sv3_ns1"]
+CASES = ["ss_ns1", "ms_ns2", "dtu_ns3", "ms_ns3_sb2", "sv3_ns1", "dtu_ns3_s6", "ms_ns2_s6"]
 TOL = 1e-4
 
 

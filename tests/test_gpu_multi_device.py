@@ -22,12 +22,15 @@ def test_multi_device_matches_single_device():
     renderer.rng_tape = {k: v.cuda() for k, v in tape.items()}
     rgb1, d1 = single(rays)
     multi = renderer.bind_parallel(net, list(range(torch.cuda.device_count())), simple_output=True).eval()
-    # the multi-device wrapper draws randoms per device: compare statistically-independent runs only
-    # for shape/finite-ness, and exactly with jitter disabled through identical per-device tapes
+    # a pre-drawn tape is split per shard: the sharded render equals the single-device one exactly (rays are independent)
+    renderer.rng_tape = {k: v.cuda() for k, v in tape.items()}
     rgbm, dm = multi(rays)
     assert rgbm.shape == rgb1.shape and dm.shape == d1.shape and rgbm.device == rgb1.device
+    assert torch.equal(rgbm, rgb1) and torch.equal(dm, d1)
+    # without a tape every device draws its own randoms: same scene, different jitter
+    rgbm, dm = multi(rays)
     assert torch.isfinite(rgbm).all() and torch.isfinite(dm).all()
-    assert maxabs(rgbm, rgb1) < 0.2  # same scene, different jitter
+    assert maxabs(rgbm, rgb1) < 0.2
     full = renderer.bind_parallel(net, [0, 1], simple_output=False).eval()(rays, want_weights=True)
     assert full["fine"]["weights"].shape == (1, B, 96)
     # weights update is picked up by the replicas

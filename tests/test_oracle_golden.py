@@ -14,7 +14,7 @@ from oracle import pixelnerf_oracle as po
 from oracle import synth
 from helpers import (N_POINTS, RENDER_SEED, load_conf, load_golden, maxabs, renderer_kwargs, sample_points)
 
-CASES = ["ss_ns1", "ms_ns2", "dtu_ns3", "ms_ns3_sb2", "sv3_ns1"]
+CASES = ["ss_ns1", "ms_ns2", "dtu_ns3", "ms_ns3_sb2", "sv3_ns1", "dtu_ns3_s6", "ms_ns2_s6"]
 
 
 @pytest.mark.parametrize("name", CASES)
