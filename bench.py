@@ -413,11 +413,10 @@ def measure(cx, wl_name, steps, warmup, profile=False, sampler=None, weak_steps=
     out_host = torch.empty(rays_step, 4).pin_memory()
 
     def step_e2e(i):
-        rgb, depth = render_views(render_par, poses, *geo, c=cam["c"], ray_batch_size=RAY_BATCH,
-                                  ray_range=ranges[i % len(ranges)], host_rays=host_rays)
+        out4 = render_views(render_par, poses, *geo, c=cam["c"], ray_batch_size=RAY_BATCH,
+                            ray_range=ranges[i % len(ranges)], host_rays=host_rays, packed=True)
         if cx.rank == 0:
-            out_host[:, :3].copy_(rgb, non_blocking=True)
-            out_host[:, 3].copy_(depth, non_blocking=True)
+            out_host.copy_(out4, non_blocking=True)   # rgb + depth of the whole frame, one contiguous copy
         torch.cuda.current_stream(dev).synchronize()
 
     ms_e2e, _, _ = timed(cx, step_e2e, steps, min(warmup, 2))
@@ -527,7 +526,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-legs", action="store_true", help="skip the secondary workloads of the default run")
     ap.add_argument("--c5-views", type=int, default=1)
@@ -563,7 +562,7 @@ def main():
         if rank == 0:
             line = {"metric": metric, "value": r5["value"], "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": warmup,
                     "ms_per_step": r5["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                    "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": config,
+                    "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision], "data": "synthetic", "config": config,
                     "gpu_launches": r5["gpu_launches"], "c5": r5}
             print(json.dumps(line), file=_json_out, flush=True)
         if world > 1:
@@ -623,7 +622,7 @@ def main():
         line = {
             "metric": metric, "value": res["value"], "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": res["ms"] / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": config,
+            "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision], "data": "synthetic", "config": config,
             "rays_per_step": R, "points_per_sec": res["value"] * POINTS_PER_RAY,
             "collective": ("ncclAllGather (torch.distributed all_gather_into_tensor) of the packed (rgb, depth) rows, %d B per step, "
                            "inside the timed region; source-view state broadcast once before it" % (R * 16)) if world > 1 else

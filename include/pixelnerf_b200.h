@@ -39,7 +39,9 @@ enum pnr_status {
 
 enum pnr_precision {
   PNR_FP32 = 0, /* validation mode: fp32 SIMT FMA everywhere (<=1e-4 vs reference) */
-  PNR_BF16 = 1  /* production mode: bf16 operands on tcgen05, fp32 accumulate      */
+  PNR_BF16 = 1, /* production mode: bf16 operands on tcgen05, fp32 accumulate      */
+  PNR_FP16 = 2  /* same kernels and MMA rate with f16 operands (11 instead of 8
+                   significand bits; values saturate at 65504), fp32 accumulate   */
 };
 
 #define PNR_MAX_LEVELS 8
@@ -56,7 +58,7 @@ typedef struct pnr_scene {
   int32_t ns;        /* views per object (num_views_per_obj)                          */
   int32_t n_levels;  /* 1 (single-scale) .. PNR_MAX_LEVELS (use_multi_scale)          */
   int32_t d_latent;  /* sum of C[i]                                                   */
-  int32_t feat_dtype; /* pnr_precision of the packed maps: fp32 or bf16, NHWC         */
+  int32_t feat_dtype; /* pnr_precision of the packed maps: fp32, bf16 or f16, NHWC    */
   int32_t C[PNR_MAX_LEVELS], H[PNR_MAX_LEVELS], W[PNR_MAX_LEVELS];
   int32_t ch_off[PNR_MAX_LEVELS]; /* first latent column of level i                   */
   float kx[PNR_MAX_LEVELS], ky[PNR_MAX_LEVELS]; /* pixel-uv -> texel scale; 1 = the
@@ -74,8 +76,8 @@ typedef struct pnr_scene {
 /*
  * One ResnetFC (src/model/resnetfc.py:65-236): lin_in, lin_z[0..n_lin_z), n_blocks x
  * ResnetBlockFC(fc_0, fc_1), lin_out.  fp32 pointers are nn.Linear tensors as-is
- * (weight (out,in) row-major, bias (out)).  `packed` is the bf16 operand image produced by
- * pnr_mlp_pack_bf16() (NULL in fp32 mode).
+ * (weight (out,in) row-major, bias (out)).  `packed` is the 16-bit operand image produced by
+ * pnr_mlp_pack() (NULL in fp32 mode) and `packed_dtype` the pnr_precision it was packed for.
  */
 typedef struct pnr_mlp {
   int32_t d_in, d_latent, d_hidden, d_out, n_blocks, combine_layer, n_lin_z;
@@ -86,6 +88,8 @@ typedef struct pnr_mlp {
   const float *fc1_w[PNR_MAX_BLOCKS], *fc1_b[PNR_MAX_BLOCKS];
   const void* packed;
   size_t packed_bytes;
+  int32_t packed_dtype; /* PNR_BF16 | PNR_FP16 */
+  int32_t reserved;
 } pnr_mlp;
 
 /* NeRFRenderer state (src/render/nerf.py:62-96). */
@@ -137,11 +141,13 @@ int pnr_profile_begin(void);
 int pnr_profile_end(double* ms, int64_t* launches, double* flops, double* bytes);
 
 /* ---- packing ------------------------------------------------------------------------- */
-/* NCHW fp32 feature map (encoder output, encoder.py:117-136) -> NHWC fp32|bf16.          */
+/* NCHW fp32 feature map (encoder output, encoder.py:117-136) -> NHWC fp32|bf16|f16.      */
 int pnr_pack_level(const float* src_nchw, int n_views, int C, int H, int W, void* dst_nhwc,
                    int dst_dtype, pnr_stream stream);
-/* bf16 operand image of one ResnetFC for the tcgen05 path.                               */
+/* 16-bit operand image of one ResnetFC for the tcgen05 path (dtype PNR_BF16 | PNR_FP16; the caller
+ * then sets mlp.packed / packed_bytes / packed_dtype).  pnr_mlp_pack_bf16 = dtype PNR_BF16.        */
 size_t pnr_mlp_packed_bytes(const pnr_mlp* mlp);
+int pnr_mlp_pack(const pnr_mlp* mlp, void* dst, size_t dst_bytes, int dtype, pnr_stream stream);
 int pnr_mlp_pack_bf16(const pnr_mlp* mlp, void* dst, size_t dst_bytes, pnr_stream stream);
 
 /* ---- kernel (a): per-(point,view) features ------------------------------------------- */

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # PIXELNERF_B200_LIB: alternative build of the same library (A/B timing of kernel variants on one box).
 LIB_PATH = os.environ.get("PIXELNERF_B200_LIB") or os.path.join(_HERE, "libpixelnerf_b200.so")
 
-FP32, BF16 = 0, 1
+FP32, BF16, FP16 = 0, 1, 2
 MAX_LEVELS, MAX_BLOCKS = 8, 8
 
 _fp = C.c_void_p
@@ -39,7 +39,7 @@ class Mlp(C.Structure):
         ("lin_z_w", _fp * MAX_BLOCKS), ("lin_z_b", _fp * MAX_BLOCKS),
         ("fc0_w", _fp * MAX_BLOCKS), ("fc0_b", _fp * MAX_BLOCKS),
         ("fc1_w", _fp * MAX_BLOCKS), ("fc1_b", _fp * MAX_BLOCKS),
-        ("packed", _fp), ("packed_bytes", C.c_size_t),
+        ("packed", _fp), ("packed_bytes", C.c_size_t), ("packed_dtype", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -72,6 +72,7 @@ EXPORTS = {
     "pnr_profile_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "pnr_pack_level": (_i, [_fp, _i, _i, _i, _i, _fp, _i, _fp]),
     "pnr_mlp_packed_bytes": (_sz, [_PM]),
+    "pnr_mlp_pack": (_i, [_PM, _fp, _sz, _i, _fp]),
     "pnr_mlp_pack_bf16": (_i, [_PM, _fp, _sz, _fp]),
     "pnr_point_features_f32": (_i, [_PS, _fp, _fp, _i, _i, _fp, _fp]),
     "pnr_net_forward_workspace": (_sz, [_PS, _PM, _i, _i, _i]),

@@ -93,7 +93,7 @@ static int validate_scene(const pnr_scene* sc) {
     off += sc->C[l];
   }
   PNR_CHECK_ARG(off == sc->d_latent, "scene.d_latent=%d but levels sum to %d", sc->d_latent, off);
-  PNR_CHECK_ARG(sc->feat_dtype == PNR_FP32 || sc->feat_dtype == PNR_BF16, "scene.feat_dtype invalid");
+  PNR_CHECK_ARG(sc->feat_dtype == PNR_FP32 || sc->feat_dtype == PNR_BF16 || sc->feat_dtype == PNR_FP16, "scene.feat_dtype invalid");
   int dz = sc->use_xyz ? 3 : 1;
   int db = dz + ((sc->use_viewdirs && sc->use_code && sc->use_code_viewdirs) ? 3 : 0);
   int d = sc->use_code ? sc->num_freqs * 2 * db + (sc->include_input ? db : 0) : db;
@@ -115,7 +115,12 @@ static int validate_mlp(const pnr_mlp* m, const pnr_scene* sc, int precision) {
                     "multi-view input with combine_layer >= n_blocks is not supported");
   }
   PNR_CHECK_ARG(m->lin_in_w && m->lin_in_b && m->lin_out_w && m->lin_out_b, "mlp linear pointers missing");
-  if (precision == PNR_BF16) PNR_CHECK_ARG(m->packed != nullptr, "mlp.packed is NULL (call pnr_mlp_pack_bf16)");
+  PNR_CHECK_ARG(precision == PNR_FP32 || precision == PNR_BF16 || precision == PNR_FP16, "precision %d invalid", precision);
+  if (precision != PNR_FP32) {
+    PNR_CHECK_ARG(m->packed != nullptr, "mlp.packed is NULL (call pnr_mlp_pack)");
+    PNR_CHECK_ARG(m->packed_dtype == precision, "mlp.packed was built for dtype %d, the call asks for %d", m->packed_dtype, precision);
+    if (sc) PNR_CHECK_ARG(sc->feat_dtype == precision, "scene.feat_dtype %d does not match precision %d", sc->feat_dtype, precision);
+  }
   return PNR_OK;
 }
 
@@ -194,7 +199,7 @@ using namespace pnr;
 
 extern "C" {
 
-int pnr_abi_version(void) { return 1; }
+int pnr_abi_version(void) { return 2; }
 const char* pnr_last_error(void) { return err_buf(); }
 int64_t pnr_launch_count(int reset) {
   int64_t v = launch_counter();
@@ -249,7 +254,7 @@ int pnr_tc_check(pnr_stream stream) { return tc_check((cudaStream_t)stream); }
 int pnr_pack_level(const float* src, int n_views, int C, int H, int W, void* dst, int dst_dtype, pnr_stream stream) {
   PNR_CHECK_ARG(src && dst, "pack_level: NULL pointer");
   PNR_CHECK_ARG(n_views > 0 && C > 0 && H > 0 && W > 0, "pack_level: bad shape");
-  PNR_CHECK_ARG(dst_dtype == PNR_FP32 || dst_dtype == PNR_BF16, "pack_level: bad dtype");
+  PNR_CHECK_ARG(dst_dtype == PNR_FP32 || dst_dtype == PNR_BF16 || dst_dtype == PNR_FP16, "pack_level: bad dtype");
   PNR_CHECK_ARG((long long)n_views * H <= 65535LL, "pack_level: n_views * H = %lld exceeds 65535 (grid z limit)",
                 (long long)n_views * H);
   return launch_pack_level(src, n_views, C, H, W, dst, dst_dtype, (cudaStream_t)stream);
@@ -257,10 +262,14 @@ int pnr_pack_level(const float* src, int n_views, int C, int H, int W, void* dst
 
 size_t pnr_mlp_packed_bytes(const pnr_mlp* mlp) { return mlp ? mlp_tc_packed_bytes(*mlp) : 0; }
 
-int pnr_mlp_pack_bf16(const pnr_mlp* mlp, void* dst, size_t dst_bytes, pnr_stream stream) {
+int pnr_mlp_pack(const pnr_mlp* mlp, void* dst, size_t dst_bytes, int dtype, pnr_stream stream) {
   PNR_TRY(validate_mlp(mlp, nullptr, PNR_FP32));
   PNR_CHECK_ARG(dst != nullptr, "mlp_pack: dst is NULL");
-  return mlp_tc_pack(*mlp, dst, dst_bytes, (cudaStream_t)stream);
+  PNR_CHECK_ARG(dtype == PNR_BF16 || dtype == PNR_FP16, "mlp_pack: dtype must be PNR_BF16 or PNR_FP16");
+  return mlp_tc_pack(*mlp, dst, dst_bytes, dtype == PNR_FP16 ? 1 : 0, (cudaStream_t)stream);
+}
+int pnr_mlp_pack_bf16(const pnr_mlp* mlp, void* dst, size_t dst_bytes, pnr_stream stream) {
+  return pnr_mlp_pack(mlp, dst, dst_bytes, PNR_BF16, stream);
 }
 
 int pnr_point_features_f32(const pnr_scene* scene, const float* xyz, const float* viewdirs, int SB, int P, float* zx,

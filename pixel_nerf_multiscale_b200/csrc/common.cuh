@@ -114,7 +114,7 @@ int launch_sample_fine_sorted(const float* rays, const float* z_coarse, const fl
                               float depth_std, int lindisp, float* z_out, cudaStream_t st);
 // mlp_tc.cu (tcgen05 path)
 size_t mlp_tc_packed_bytes(const pnr_mlp& m);
-int mlp_tc_pack(const pnr_mlp& m, void* dst, size_t dst_bytes, cudaStream_t st);
+int mlp_tc_pack(const pnr_mlp& m, void* dst, size_t dst_bytes, int fmt /* 0 bf16, 1 f16 */, cudaStream_t st);
 size_t net_tc_workspace(const pnr_scene& sc, const pnr_mlp& m, int SB, long long P);
 int net_forward_tc(const pnr_scene& sc, const pnr_mlp& m, const float* xyz, const float* viewdirs,
                    const float* rays, const float* z, int K, int SB, long long P, float* out, void* ws,

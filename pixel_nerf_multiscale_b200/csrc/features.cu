@@ -1,4 +1,8 @@
 // Kernel (a), fp32 validation variant, and the NCHW -> NHWC pyramid packer.
+#include <cuda_fp16.h>
+
+#include <type_traits>
+
 #include "features.cuh"
 
 namespace pnr {
@@ -25,6 +29,8 @@ __global__ void pack_level_kernel(const float* __restrict__ src, int C, int H, i
       size_t o = (((size_t)view * H + y) * W + x) * C + c;
       if constexpr (sizeof(OutT) == 4)
         dst[o] = v;
+      else if constexpr (std::is_same<OutT, __half>::value)
+        dst[o] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
       else
         dst[o] = __float2bfloat16(v);
     }
@@ -35,6 +41,8 @@ int launch_pack_level(const float* src, int n_views, int C, int H, int W, void* 
   dim3 block(32, 8), grid(ceil_div(W, 32), ceil_div(C, 32), n_views * H);
   if (dtype == PNR_FP32)
     pack_level_kernel<float><<<grid, block, 0, st>>>(src, C, H, W, (float*)dst);
+  else if (dtype == PNR_FP16)
+    pack_level_kernel<__half><<<grid, block, 0, st>>>(src, C, H, W, (__half*)dst);
   else
     pack_level_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(src, C, H, W, (__nv_bfloat16*)dst);
   PNR_LAUNCHED();
@@ -100,6 +108,7 @@ int launch_point_features_f32(const pnr_scene& sc, const float* xyz, const float
   int wpb = 8;
   long long blocks = ceil_div_ll(rows, wpb);
   PNR_CHECK_ARG(blocks < 2147483647LL, "point_features: too many rows (%lld)", rows);
+  PNR_UNSUPPORTED(sc.feat_dtype == PNR_FP16, "point_features_f32 reads fp32 or bf16 maps");
   if (sc.feat_dtype == PNR_FP32)
     point_features_f32_kernel<float><<<(unsigned)blocks, wpb * 32, 0, st>>>(sc, xyz, viewdirs, rays, z, K, SB, P, zx);
   else

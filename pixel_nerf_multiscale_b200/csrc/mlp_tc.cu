@@ -126,6 +126,7 @@ struct PackJob {
   int K;            // valid K columns of this source
   int k_slices;     // 64-wide slices this source occupies
   uint32_t dst_off; // byte offset of its first chunk
+  int fmt;          // 0 = bf16, 1 = f16
 };
 
 __global__ void pack_weights_kernel(PackJob job, uint8_t* __restrict__ dst) {
@@ -145,7 +146,7 @@ __global__ void pack_weights_kernel(PackJob job, uint8_t* __restrict__ dst) {
   for (int e = 0; e < 4; ++e) {
     float lo = (k0 + 2 * e < job.K) ? job.w[(size_t)n * job.K + k0 + 2 * e] : 0.f;
     float hi = (k0 + 2 * e + 1 < job.K) ? job.w[(size_t)n * job.K + k0 + 2 * e + 1] : 0.f;
-    v[e] = pack_bf16x2(lo, hi);
+    v[e] = job.fmt == 1 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
   }
   *reinterpret_cast<uint4*>(dst + job.dst_off + idx * 16) = make_uint4(v[0], v[1], v[2], v[3]);
 }
@@ -209,14 +210,14 @@ size_t mlp_tc_packed_bytes(const pnr_mlp& m) {
   return make_layout(m).total;
 }
 
-int mlp_tc_pack(const pnr_mlp& m, void* dst, size_t dst_bytes, cudaStream_t st) {
+int mlp_tc_pack(const pnr_mlp& m, void* dst, size_t dst_bytes, int fmt, cudaStream_t st) {
   PNR_TRY(tc_supported(m));
   Layout L = make_layout(m);
   PNR_CHECK_ARG(dst_bytes >= L.total, "mlp_pack: destination too small (%zu < %zu)", dst_bytes, L.total);
   PNR_CHECK_ARG(((uintptr_t)dst & 15) == 0, "mlp_pack: destination must be 16-byte aligned");
   uint8_t* d = (uint8_t*)dst;
   auto pack = [&](const float* w, int K, int slices, uint32_t off) -> int {
-    PackJob j{w, K, slices, off};
+    PackJob j{w, K, slices, off, fmt};
     long long total = (long long)slices * 4 * 8 * 128;
     pack_weights_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(j, d);
     PNR_LAUNCHED();
@@ -257,11 +258,13 @@ int mlp_tc_pack(const pnr_mlp& m, void* dst, size_t dst_bytes, cudaStream_t st) 
 // kernel (a), bf16 operand variant (gather warps of the fused kernel): [latent | code] straight into the
 // A-tile operand image  zc[slot][cta][k-group][row][8 bf16]
 // =============================================================================================
-__device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+template <int FMT>
+__device__ __forceinline__ void x8_to_float(const uint4& u, float (&f)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(h[i]);
+    float2 t;
+    if constexpr (FMT == 1) t = __half22float2(reinterpret_cast<const __half2*>(&u)[i]);
+    else t = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(&u)[i]);
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
   }
@@ -330,6 +333,7 @@ __device__ __forceinline__ Taps make_taps_fast(float u, float v, int H, int W, f
 // over the 8-channel groups (4 scattered 128-bit tap loads each; adjacent groups share 32-B sectors
 // through L1) and over the code groups, and writes 16-byte operand entries -- a warp stores 512
 // contiguous bytes per group.
+template <int FMT>
 __device__ __forceinline__ void gather_row_to_zc(const pnr_scene& sc, const float* __restrict__ xyz,
                                                  const float* __restrict__ viewdirs, const float* __restrict__ rays,
                                                  const float* __restrict__ z, int K, long long gp, int v, bool valid,
@@ -367,16 +371,16 @@ __device__ __forceinline__ void gather_row_to_zc(const pnr_scene& sc, const floa
     for (int g = 0; g < C8; ++g) {
       const uint4 q00 = __ldg(p00 + g), q01 = __ldg(p01 + g), q10 = __ldg(p10 + g), q11 = __ldg(p11 + g);
       float a[8], b[8], c[8], d[8];
-      bf16x8_to_float(q00, a);
-      bf16x8_to_float(q01, b);
-      bf16x8_to_float(q10, c);
-      bf16x8_to_float(q11, d);
+      x8_to_float<FMT>(q00, a);
+      x8_to_float<FMT>(q01, b);
+      x8_to_float<FMT>(q10, c);
+      x8_to_float<FMT>(q11, d);
       uint32_t o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float lo = a[2 * e] * t.w00 + b[2 * e] * t.w01 + c[2 * e] * t.w10 + d[2 * e] * t.w11;
         float hi = a[2 * e + 1] * t.w00 + b[2 * e + 1] * t.w01 + c[2 * e + 1] * t.w10 + d[2 * e + 1] * t.w11;
-        o[e] = pack_bf16x2(lo, hi);
+        o[e] = pack2<FMT>(lo, hi);
       }
       *reinterpret_cast<uint4*>(dst + (size_t)g * 1024) = make_uint4(o[0], o[1], o[2], o[3]);
     }
@@ -395,7 +399,7 @@ __device__ __forceinline__ void gather_row_to_zc(const pnr_scene& sc, const floa
     uint32_t o[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e)
-      o[e] = pack_bf16x2(code_entry_fast(cc, pc, g * 8 + 2 * e), code_entry_fast(cc, pc, g * 8 + 2 * e + 1));
+      o[e] = pack2<FMT>(code_entry_fast(cc, pc, g * 8 + 2 * e), code_entry_fast(cc, pc, g * 8 + 2 * e + 1));
     *reinterpret_cast<uint4*>(base + (size_t)(nks_z * 8 + g) * 1024) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
@@ -403,7 +407,7 @@ __device__ __forceinline__ void gather_row_to_zc(const pnr_scene& sc, const floa
 // fp32 rows in reference order (sb, ns, p) -> operand image (used by pnr_mlp_forward in bf16 mode)
 __global__ void __launch_bounds__(256)
 rows_to_operand_kernel(const float* __restrict__ zx, int d_latent, int d_in, int SB, int NS, long long Pper, int ppw,
-                       int tilesA, int nks_z, int nks_c, uint8_t* __restrict__ zc) {
+                       int tilesA, int nks_z, int nks_c, int fmt, uint8_t* __restrict__ zc) {
   const int lane = threadIdx.x & 31;
   const long long wrow = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (wrow >= (long long)tilesA * 128) return;
@@ -431,7 +435,7 @@ rows_to_operand_kernel(const float* __restrict__ zx, int d_latent, int d_in, int
       for (int e = 0; e < 4; ++e) {
         float lo = (k0 + 2 * e < lim) ? s[k0 + 2 * e] : 0.f;
         float hi = (k0 + 2 * e + 1 < lim) ? s[k0 + 2 * e + 1] : 0.f;
-        o[e] = pack_bf16x2(lo, hi);
+        o[e] = fmt == 1 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
       }
     }
     *reinterpret_cast<uint4*>(base + (size_t)g * 1024) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -480,6 +484,7 @@ struct Ctx {
   uint32_t tmem;
   uint32_t rank;
   int* err;
+  uint32_t idesc;  // tcgen05 instruction descriptor (operand format, M=128, N=256)
   long long w[6];  // cycles spent waiting, by class (debug statistics)
   __device__ __forceinline__ uint32_t bar(int i) const { return bars + i * 8; }
 };
@@ -553,6 +558,7 @@ __device__ __forceinline__ uint32_t wchunk(uint32_t off, int s, int nb, uint32_t
 // (both complete on its barrier), issues 4 MMAs (K=64) and releases the slot in both CTAs.
 template <bool SM>
 __device__ __forceinline__ void mma_step_b(Ctx& cx, Ring& rb, uint32_t a_addr, uint32_t d_col, bool first) {
+  // (cx.idesc: instruction descriptor of the kernel's operand format, M=128 N=256)
   twait(cx, 0, rb.full_bar(), rb.phase, 301);
   if (cx.rank == 0) {
 #if PNR_TC_STATS
@@ -562,7 +568,7 @@ __device__ __forceinline__ void mma_step_b(Ctx& cx, Ring& rb, uint32_t a_addr, u
 #ifdef PNR_EXP_N64  // timing experiment: quarter-size MMAs (results are garbage)
     const uint32_t idesc = idesc_bf16_f32(128, 64);
 #else
-    const uint32_t idesc = idesc_bf16_f32(128, 256);
+    const uint32_t idesc = cx.idesc;
 #endif
     const uint32_t b_addr = cx.smem + OFF_BRING + rb.idx * B_CHUNK;
     const uint64_t da0 = smem_desc(a_addr, ROWS * 16, 128);
@@ -668,7 +674,8 @@ __device__ __forceinline__ void prefetch_bias(BiasRegs& b, const Epi& e, const f
   }
 }
 
-// TMEM (64 columns of block nb) -> relu(v + bias) -> bf16 operand panels in `dst_off`; publishes slice
+// TMEM (64 columns of block nb) -> relu(v + bias) -> 16-bit operand panels in `dst_off`; publishes slice
+template <int FMT>
 __device__ __forceinline__ void epi_to_operand(const Ctx& cx, const Epi& e, uint32_t col, int nb, const BiasRegs& bias,
                                                uint32_t dst_off, int ready_bar0) {
 #pragma unroll
@@ -686,8 +693,8 @@ __device__ __forceinline__ void epi_to_operand(const Ctx& cx, const Epi& e, uint
       float v6 = fmaxf(__uint_as_float(r[8 * j + 6]) + bb.z, 0.f), v7 = fmaxf(__uint_as_float(r[8 * j + 7]) + bb.w, 0.f);
       uint32_t kg = (uint32_t)(f0 >> 3) + j;
       uint32_t addr = cx.smem + dst_off + kg * (ROWS * 16) + e.row * 16;
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(v0, v1)),
-                   "r"(pack_bf16x2(v2, v3)), "r"(pack_bf16x2(v4, v5)), "r"(pack_bf16x2(v6, v7))
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack2<FMT>(v0, v1)),
+                   "r"(pack2<FMT>(v2, v3)), "r"(pack2<FMT>(v4, v5)), "r"(pack2<FMT>(v6, v7))
                    : "memory");
     }
   }
@@ -825,6 +832,7 @@ constexpr int OFF_PART = OFF_SX + 8704;                // [4 outputs][4 column p
 
 // pooled rows of this CTA's staging buffer -> TMEM residual at column `xc` (fp32) and, with `to_sx`,
 // relu -> bf16 operand in S_x (publishing the 8 K slices)
+template <int FMT>
 __device__ __noinline__ void load_x_tile(const Params& p, const Ctx cx, const Epi e, uint32_t xc, bool valid, bool to_sx) {
   const float4* stage4 = reinterpret_cast<const float4*>(p.stage) + (size_t)blockIdx.x * (ROWS * DH / 4);
 #pragma unroll 1
@@ -851,8 +859,8 @@ __device__ __noinline__ void load_x_tile(const Params& p, const Ctx cx, const Ep
           uint32_t kg = (uint32_t)(f0 >> 3) + j;
           uint32_t addr = cx.smem + OFF_SX + kg * (ROWS * 16) + e.row * 16;
           auto rl = [&](int i) { return fmaxf(__uint_as_float(r[8 * j + i]), 0.f); };
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(rl(0), rl(1))),
-                       "r"(pack_bf16x2(rl(2), rl(3))), "r"(pack_bf16x2(rl(4), rl(5))), "r"(pack_bf16x2(rl(6), rl(7)))
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack2<FMT>(rl(0), rl(1))),
+                       "r"(pack2<FMT>(rl(2), rl(3))), "r"(pack2<FMT>(rl(4), rl(5))), "r"(pack2<FMT>(rl(6), rl(7)))
                        : "memory");
         }
       }
@@ -941,7 +949,7 @@ __device__ __noinline__ void head_tile(const Params& p, Ctx cx, const Epi e, uin
 // =============================================================================================
 // The fused kernel
 // =============================================================================================
-template <bool SM>
+template <bool SM, int FMT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Ctx cx;
@@ -949,6 +957,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
   cx.bars = cx.smem + OFF_BARS;
   cx.rank = cluster_ctarank();
   cx.err = p.err;
+  cx.idesc = FMT == 1 ? idesc_f16_f32(128, 256) : idesc_bf16_f32(128, 256);
   for (int i = 0; i < 6; ++i) cx.w[i] = 0;
   const long long t_begin = clock64();
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + OFF_BARS + N_BARS * 8);
@@ -1083,7 +1092,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
         if (git >= 1) twait(cx, 2, cx.bar(ZC_TAKEN), (git - 1) & 1, 204);
         const size_t zslot = p.zc_ring ? (size_t)pair * p.zc_ring + git % p.zc_ring : (size_t)tile;
         uint8_t* base = const_cast<uint8_t*>(p.zc) + ((zslot * 2 + cx.rank) * nsl) * A_SLICE + (size_t)row * 16;
-        gather_row_to_zc(p.sc, p.xyz, p.viewdirs, p.rays, p.zsamp, p.K, gp, v, valid, p.nks_z, p.nks_c, base);
+        gather_row_to_zc<FMT>(p.sc, p.xyz, p.viewdirs, p.rays, p.zsamp, p.K, gp, v, valid, p.nks_z, p.nks_c, base);
         // generic-proxy global writes -> visible to the async proxy (TMA) of this SM before the signal.  (The wait
         // above also keeps ZC_READY from completing twice before the producer looks.)
         __threadfence();
@@ -1111,7 +1120,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
             twait(cx, 0, cx.bar(X_READY + nb), xph, 401 + nb * 1000 + (int)tc * 10000 + warp * 1000000 + (int)cx.rank * 100000000);
             tc_fence_after();
             t0 = clock64();
-            epi_to_operand(cx, e, xcol, nb, br, OFF_SX, SX_READY);
+            epi_to_operand<FMT>(cx, e, xcol, nb, br, OFF_SX, SX_READY);
             cx.w[2] += clock64() - t0;
           }
           xph ^= 1;
@@ -1120,7 +1129,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
             twait(cx, 1, cx.bar(NET_READY + nb), nph, 402 + nb);
             tc_fence_after();
             t0 = clock64();
-            epi_to_operand(cx, e, netcol, nb, br, OFF_H, H_READY);
+            epi_to_operand<FMT>(cx, e, netcol, nb, br, OFF_H, H_READY);
             cx.w[3] += clock64() - t0;
           }
           nph ^= 1;
@@ -1149,7 +1158,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
         const long long gp = (long long)((group_tile0 + kk * npairs) * 2 + (int)cx.rank) * p.ppw + pl;
         const bool valid = kk < k && gp < p.P;
         asm volatile("bar.sync 1, 256;" ::: "memory");  // all pooled rows of this CTA are written
-        load_x_tile(p, cx, e, xcol, valid, p.n_post > 0);
+        load_x_tile<FMT>(p, cx, e, xcol, valid, p.n_post > 0);
         for (int j = 0; j < p.n_post; ++j) {
           const int b = p.n_pre + j;
           BiasRegs br;
@@ -1157,7 +1166,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
             prefetch_bias(br, e, bias0 + (size_t)b * DH, nb);
             twait(cx, 1, cx.bar(NET_READY + nb), nph, 502 + nb);
             tc_fence_after();
-            epi_to_operand(cx, e, netcol, nb, br, OFF_H, H_READY);
+            epi_to_operand<FMT>(cx, e, netcol, nb, br, OFF_H, H_READY);
           }
           nph ^= 1;
           if (j + 1 < p.n_post) {
@@ -1165,7 +1174,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
               prefetch_bias(br, e, biasB + (size_t)(j + 1) * DH, nb);
               twait(cx, 0, cx.bar(X_READY + nb), xph, 501);
               tc_fence_after();
-              epi_to_operand(cx, e, xcol, nb, br, OFF_SX, SX_READY);
+              epi_to_operand<FMT>(cx, e, xcol, nb, br, OFF_SX, SX_READY);
             }
             xph ^= 1;
           }
@@ -1201,7 +1210,7 @@ struct DeviceState {
   int* err_host = nullptr;  // [0] fault tag (0 = none), [1] wait timeout in ms (0 = never give up)
   int* err_dev = nullptr;
   int sms = 0;
-  bool attr_set[2] = {false, false};
+  bool attr_set[4] = {false, false, false, false};
 };
 static std::mutex g_dev_mutex;
 static DeviceState g_dev[PNR_MAX_DEVICES];
@@ -1338,13 +1347,15 @@ static int cached_tmap(CUtensorMap* out, const void* base, size_t bytes, int box
   return PNR_OK;
 }
 
-static int launch_cluster(DeviceState& d, bool solo, int pairs, const Params& p, cudaStream_t st) {
-  void (*kern)(const Params) = solo ? mlp_fused_kernel<true> : mlp_fused_kernel<false>;
+static int launch_cluster(DeviceState& d, bool solo, int fmt, int pairs, const Params& p, cudaStream_t st) {
+  void (*kern)(const Params) = fmt == 1 ? (solo ? mlp_fused_kernel<true, 1> : mlp_fused_kernel<false, 1>)
+                                        : (solo ? mlp_fused_kernel<true, 0> : mlp_fused_kernel<false, 0>);
   {
     std::lock_guard<std::mutex> lock(g_dev_mutex);
-    if (!d.attr_set[solo ? 1 : 0]) {
+    const int slot = (fmt == 1 ? 2 : 0) + (solo ? 1 : 0);
+    if (!d.attr_set[slot]) {
       PNR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      d.attr_set[solo ? 1 : 0] = true;
+      d.attr_set[slot] = true;
     }
   }
   cudaLaunchConfig_t cfg;
@@ -1365,7 +1376,7 @@ struct GatherArgs {
 };
 
 static int run_fused(DeviceState& d, const pnr_mlp& m, const Layout& L, const Plan& pl, int ns, long long P, float* out,
-                     int head, cudaStream_t st, const GatherArgs* ga = nullptr) {
+                     int head, int fmt, cudaStream_t st, const GatherArgs* ga = nullptr) {
   PNR_TRY(take_fault(d, "reported before the next launch"));
   // algorithmic work (2*MACs of the nn.Linear layers, unpadded)
   const double mac_pre = (double)m.d_in * DH + (double)L.n_pre * m.d_latent * DH + 2.0 * L.n_pre * DH * DH;
@@ -1414,7 +1425,7 @@ static int run_fused(DeviceState& d, const pnr_mlp& m, const Layout& L, const Pl
     // issuer mode by latent width (see mma_elect): PNR_SOLO_MMA=0/1 forces one of them
     static const int force = [] { const char* e = getenv("PNR_SOLO_MMA"); return e ? atoi(e) : -1; }();
     const bool solo = force >= 0 ? force != 0 : L.nks_z <= 4;
-    PNR_TRY(launch_cluster(d, solo, pl.pairs, p, st));
+    PNR_TRY(launch_cluster(d, solo, fmt, pl.pairs, p, st));
   }
   return PNR_OK;
 }
@@ -1452,7 +1463,9 @@ int net_forward_tc(const pnr_scene& sc, const pnr_mlp& m, const float* xyz, cons
   PNR_TRY(tc_supported(m));
   PNR_CHECK_ARG(SB == 1, "net_forward_tc: one object per call");
   PNR_UNSUPPORTED(sc.ns > 32, "more than 32 source views per object");
-  PNR_UNSUPPORTED(sc.feat_dtype != PNR_BF16, "bf16 path needs a bf16-packed pyramid");
+  PNR_UNSUPPORTED(sc.feat_dtype != PNR_BF16 && sc.feat_dtype != PNR_FP16, "tensor-core path needs a bf16- or f16-packed pyramid");
+  PNR_CHECK_ARG(m.packed_dtype == sc.feat_dtype, "mlp.packed was built for dtype %d, the feature pyramid for %d", m.packed_dtype,
+                sc.feat_dtype);
   for (int l = 0; l < sc.n_levels; ++l)
     PNR_UNSUPPORTED(sc.C[l] % 8 != 0 || sc.ch_off[l] % 8 != 0, "bf16 gather needs channel counts that are multiples of 8");
   PNR_CHECK_ARG(m.packed_bytes >= make_layout(m).total, "mlp.packed image too small");
@@ -1467,7 +1480,7 @@ int net_forward_tc(const pnr_scene& sc, const pnr_mlp& m, const float* xyz, cons
     return PNR_ERR_WORKSPACE;
   }
   GatherArgs ga{&sc, xyz, viewdirs, rays, z, K};
-  return run_fused(*d, m, L, pl, sc.ns, P, out, 1, st, &ga);
+  return run_fused(*d, m, L, pl, sc.ns, P, out, 1, sc.feat_dtype == PNR_FP16 ? 1 : 0, st, &ga);
 }
 
 size_t mlp_tc_rows_workspace(const pnr_mlp& m, int SB, int NS, int P) {
@@ -1494,10 +1507,11 @@ int mlp_forward_tc_rows(const pnr_mlp& m, const float* zx, int SB, int NS, int P
     return PNR_ERR_WORKSPACE;
   }
   long long wrows = (long long)pl.tilesA * 128;
+  const int fmt = m.packed_dtype == PNR_FP16 ? 1 : 0;
   rows_to_operand_kernel<<<(unsigned)ceil_div_ll(wrows, 8), 256, 0, st>>>(zx, m.d_latent, m.d_in, SB, NS, P, pl.ppw,
-                                                                        pl.tilesA, L.nks_z, L.nks_c, pl.zc);
+                                                                        pl.tilesA, L.nks_z, L.nks_c, fmt, pl.zc);
   PNR_LAUNCHED();
-  return run_fused(*d, m, L, pl, NS, pts, out, 0, st);
+  return run_fused(*d, m, L, pl, NS, pts, out, 0, fmt, st);
 }
 
 }  // namespace pnr

@@ -3,6 +3,7 @@
 // Everything here is sm_100a-only; there is no fallback path.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace pnr {
@@ -192,10 +193,14 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
   d |= (uint64_t)1 << 46;
   return d;
 }
-// instruction descriptor for kind::f16: bf16 x bf16 -> f32, both operands K-major
+// instruction descriptor for kind::f16: bf16 x bf16 -> f32 (or f16 x f16 -> f32), both operands K-major.
+// a_format / b_format: 0 = f16, 1 = bf16.
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
   return (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t idesc_f16_f32(int M, int N) {
+  return (1u << 4) /*D=f32*/ | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 template <int CG>
 __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -257,6 +262,17 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// f16 pair, round-to-nearest, saturating at +-65504 instead of overflowing to inf
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// operand element format of the tensor-core path: 0 = bf16, 1 = f16 (same MMA rate; f16 carries 11
+// significand bits instead of 8, in exchange for range: activations and features must stay below 65504)
+template <int FMT> __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  if constexpr (FMT == 1) return pack_f16x2(lo, hi); else return pack_bf16x2(lo, hi);
 }
 
 }  // namespace ptx

@@ -22,7 +22,8 @@ from .code import PositionalEncoding
 from .encoder import ImageEncoder
 from .model_util import make_encoder, make_mlp
 
-_PRECISIONS = {"bf16": N.BF16, "fp32": N.FP32}
+_PRECISIONS = {"bf16": N.BF16, "fp32": N.FP32, "fp16": N.FP16}
+_TORCH_DTYPE = {N.FP32: torch.float32, N.BF16: torch.bfloat16, N.FP16: torch.float16}
 
 
 class PixelNeRFNet(torch.nn.Module):
@@ -70,7 +71,8 @@ class PixelNeRFNet(torch.nn.Module):
         self.num_views_per_obj = 1
 
         # native-path state
-        self.precision = os.environ.get("PIXELNERF_B200_PRECISION", "bf16")
+        # "fp16" (default) | "bf16": tensor-core path with f16 / bf16 operands; "fp32": validation path
+        self.precision = os.environ.get("PIXELNERF_B200_PRECISION", "fp16")
         self.texel_scale = None  # None = the fork's pixel==texel behaviour
         self._scene_cache = {}
         self._scene_version = 0
@@ -135,7 +137,7 @@ class PixelNeRFNet(torch.nn.Module):
     def _native_precision(self, precision=None):
         p = self.precision if precision is None else precision
         if p not in _PRECISIONS:
-            raise ValueError("precision must be 'bf16' or 'fp32', got %r" % (p,))
+            raise ValueError("precision must be 'bf16', 'fp16' or 'fp32', got %r" % (p,))
         return _PRECISIONS[p]
 
     def _per_view(self, t, n_views):
@@ -180,8 +182,7 @@ class PixelNeRFNet(torch.nn.Module):
                 fm = fm.detach().float().contiguous()
                 v, ch, h, w = fm.shape
                 assert v == n_views, "feature maps have %d views, cameras %d" % (v, n_views)
-                packed = torch.empty((v, h, w, ch), dtype=torch.float32 if prec == N.FP32 else torch.bfloat16,
-                                     device=device)
+                packed = torch.empty((v, h, w, ch), dtype=_TORCH_DTYPE[prec], device=device)
                 N.check(lib.pnr_pack_level(N.ptr(fm), v, ch, h, w, N.ptr(packed), prec, N.stream_ptr(device)),
                         "pnr_pack_level")
                 keep += [fm, packed]

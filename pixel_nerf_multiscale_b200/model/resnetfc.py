@@ -131,14 +131,14 @@ class ResnetFC(nn.Module):
         for i, blk in enumerate(self.blocks):
             m.fc0_w[i], m.fc0_b[i] = dev(blk.fc_0.weight), dev(blk.fc_0.bias)
             m.fc1_w[i], m.fc1_b[i] = dev(blk.fc_1.weight), dev(blk.fc_1.bias)
-        if precision == N.BF16:
+        if precision != N.FP32:
             device = self.lin_in.weight.device
             nbytes = N.lib().pnr_mlp_packed_bytes(m)
             packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
             with torch.cuda.device(device):
-                N.check(N.lib().pnr_mlp_pack_bf16(m, N.ptr(packed), nbytes, N.stream_ptr(device)), "pnr_mlp_pack_bf16")
+                N.check(N.lib().pnr_mlp_pack(m, N.ptr(packed), nbytes, precision, N.stream_ptr(device)), "pnr_mlp_pack")
             keep.append(packed)
-            m.packed, m.packed_bytes = N.ptr(packed), nbytes
+            m.packed, m.packed_bytes, m.packed_dtype = N.ptr(packed), nbytes, precision
         self._native_cache[precision] = (fp, m, keep)
         return m, keep
 

@@ -65,7 +65,7 @@ def gather_outputs(t, total, dim=1, group=None):
 
 
 def render_views(render_par, poses, width, height, focal, z_near, z_far, c=None, ray_batch_size=50000,
-                 rank=None, world=None, gather=True, group=None, ray_range=None, host_rays=None):
+                 rank=None, world=None, gather=True, group=None, ray_range=None, host_rays=None, packed=False):
     """The frame loop of the reference's drivers (eval/gen_video.py:174-237, eval/eval.py:250-292)
     with the rays generated where they are rendered: every rank derives ITS contiguous
     range of the NV*H*W rays from (poses, focal, c) -- no (NV,H,W,8) host tensor, no scatter --
@@ -78,6 +78,8 @@ def render_views(render_par, poses, width, height, focal, z_near, z_far, c=None,
            drivers' ``torch.split(render_rays.view(-1, 8), ray_batch_size)`` batches cross frame borders)
     :param host_rays optional (NV*H*W, 8) CPU tensor (pinned): take the rays from the host like the
            reference's drivers do (``util.gen_rays(...).to(device)``), copying only this rank's slice
+    :param packed return the gathered rows as ONE contiguous (n, 4) tensor [r g b depth] (a single D2H copy
+           moves a frame to the host)
     :return rgb (NV,H,W,3), depth (NV,H,W); with ``ray_range`` flat (n,3), (n,); without ``gather``
             this rank's flat slices (n,3), (n,) and its [lo, hi) ray range
     """
@@ -110,6 +112,8 @@ def render_views(render_par, poses, width, height, focal, z_near, z_far, c=None,
         return out4[:, :3], out4[:, 3], (lo, hi)
     if world > 1:
         out4 = gather_outputs(out4.contiguous(), total, dim=0, group=group)
+    if packed:
+        return out4
     if ray_range is not None:
         return out4[:, :3], out4[:, 3]
     return out4[:, :3].reshape(nv, height, width, 3), out4[:, 3].reshape(nv, height, width)

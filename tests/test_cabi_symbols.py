@@ -28,7 +28,7 @@ def test_abi_version_and_error_string_without_gpu():
     from pixel_nerf_multiscale_b200 import _native as N
 
     lib = N.lib()
-    assert lib.pnr_abi_version() == 1
+    assert lib.pnr_abi_version() == 2
     assert isinstance(lib.pnr_last_error(), bytes)
     # argument validation happens before any CUDA call: NULL scene -> BAD_ARG, message set
     st = lib.pnr_point_features_f32(None, None, None, 1, 1, None, None)
@@ -40,6 +40,6 @@ def test_struct_layouts_match_header_sizes():
     from pixel_nerf_multiscale_b200 import _native as N
 
     assert ctypes.sizeof(N.Scene) == 5 * 4 + 4 * 8 * 4 + 2 * 8 * 4 + 4 + 8 * 8 + 8 + 9 * 4 + 4  # incl. padding
-    assert ctypes.sizeof(N.Mlp) == 8 * 4 + 4 * 8 + 6 * 8 * 8 + 8 + 8
+    assert ctypes.sizeof(N.Mlp) == 8 * 4 + 4 * 8 + 6 * 8 * 8 + 8 + 8 + 2 * 4
     assert ctypes.sizeof(N.RenderCfg) == 8 * 4
     assert ctypes.sizeof(N.RngTape) == 4 * 8 and ctypes.sizeof(N.RenderOut) == 8 * 8

@@ -74,8 +74,9 @@ def test_fullsize_bf16_properties(workload):
     assert 0.05 < alpha.mean().item() < 0.999 and full["fine"].rgb.std().item() > 1e-3
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
 @pytest.mark.parametrize("workload,gain", [("c2", 1.0), ("c3", 1.0), ("c4", 1.0), ("c2", 6.0), ("c3", 6.0), ("c4", 12.0)])
-def test_fullsize_bf16_vs_oracle_on_cuda(workload, gain):
+def test_fullsize_bf16_vs_oracle_on_cuda(workload, gain, precision):
     """BASELINE.json's configurations (full-size feature maps, real camera geometry) at 8 192 rays: the bf16
     tensor-core path against the fp32 ORACLE on the same GPU and the same random draws, asserting the MAX
     (north_star: per-pixel rgb/depth max-abs <= 1e-2, |dPSNR| <= 0.05 dB), at the synthetic head's density
@@ -85,7 +86,7 @@ def test_fullsize_bf16_vs_oracle_on_cuda(workload, gain):
 
     from sigma_sweep import compare
 
-    r = compare(workload, gain, 8192)
+    r = compare(workload, gain, 8192, precision=precision)
     print(json.dumps(r))
     out = os.path.join(REPO, "gpurun_out")
     if os.path.isdir(out):

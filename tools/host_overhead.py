@@ -14,7 +14,7 @@ import bench  # noqa: E402
 
 wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "c1"]
 dev = torch.device("cuda:0")
-net, renderer, conf, cam = bench.build_scene(wl, dev, "bf16")
+net, renderer, conf, cam = bench.build_scene(wl, dev, "fp16")
 par = renderer.bind_parallel(net, [0], simple_output=True).eval()
 rays = bench.orbit_rays(wl, cam, 1, dev)[:4096].contiguous()[None]
 with torch.no_grad():
