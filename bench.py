@@ -488,7 +488,7 @@ def roofline(res, peaks):
            "figure beside it)") if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     ach = pf[1] / (pms[1] * 1e-3) / 1e12
     traffic, tnote = None, None
-    for cand in ("r02_ncu_summary.json", "r01_v13_ncu_summary.json"):
+    for cand in ("r02_ncu_summary.json", "r02v1_ncu_summary.json", "r01_v13_ncu_summary.json"):
         try:  # DRAM bytes of one launch of this kernel from the committed ncu --set full capture
             prof_j = json.load(open(os.path.join(REPO, "profiles", cand)))
             k = next(v for n, v in prof_j.items() if n.startswith("mlp_phaseA") or n.startswith("mlp_fused"))

@@ -287,23 +287,61 @@ int launch_fine_indices(const float* cdf, const float* u, int B, int Kc, int Kf,
 }
 
 // ---- sample_fine + sample_fine_depth + cat + sort -------------------------------------------------
-// smem per warp: cdf[Kc+1] followed by the sort buffer [Kpad] (Kpad = next pow2 >= Kc + n_fine).
+// One warp per ray.  smem per warp: cdf[Kc+1] followed by the sort buffer [Kpad] (Kpad = next pow2 >= Kc + n_fine).
+//   * cdf: the divisions pdf = (w + 1e-5) / sum run on all lanes; the running sum itself stays ONE sequential fp32
+//     chain (c_k = c_{k-1} + pdf_k, the order of torch.cumsum on a CPU row), executed by lane 0 on registers --
+//     the bin search depends on the last bit of every cdf entry;
+//   * sort: the coarse samples arrive ascending (stratified), so only the n_fine new samples are sorted (one per
+//     lane, a 15-step shuffle bitonic network) and the two sorted lists are merged by rank: position = own index +
+//     number of elements of the other list before it (ties: coarse first).  If a rounding inversion left the
+//     coarse list unsorted, or n_fine > 32, the general shared-memory bitonic sort of all Kpad values runs instead.
+__device__ __forceinline__ float warp_sort32(float v, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const float o = __shfl_xor_sync(0xffffffffu, v, stride);
+      const bool up = (lane & size) == 0;          // ascending block
+      const bool lower = (lane & stride) == 0;     // this lane keeps the smaller value of the pair when ascending
+      const float mn = fminf(v, o), mx = fmaxf(v, o);
+      v = (lower == up) ? mn : mx;
+    }
+  }
+  return v;
+}
+
 __global__ void __launch_bounds__(256)
 sample_fine_sorted_kernel(const float* __restrict__ rays, const float* __restrict__ z_coarse,
                           const float* __restrict__ weights, const float* __restrict__ depth,
                           const float* __restrict__ fine_u, const float* __restrict__ fine_jit,
                           const float* __restrict__ depth_nrm, int B, int Kc, int n_imp, int n_dep, float depth_std,
-                          int lindisp, int Kpad, float* __restrict__ z_out) {
+                          int lindisp, int Kpad, int Kbuf, float* __restrict__ z_out) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = blockIdx.x * (blockDim.x >> 5) + warp;
   if (r >= B) return;  // whole warp exits together
-  float* cdf = smem + (size_t)warp * (Kc + 1 + Kpad);
+  float* cdf = smem + (size_t)warp * (Kc + 1 + Kbuf);  // Kbuf = max(Kpad, Kc + 32) floats of sort / merge buffer
   float* buf = cdf + Kc + 1;
   const float near = rays[(size_t)r * 8 + 6], far = rays[(size_t)r * 8 + 7];
-  const int K = Kc + n_imp + n_dep;
+  const int n_fine = n_imp + n_dep, K = Kc + n_fine;
+  const bool fast = n_fine <= 32;
+  // fast path: this lane's random inputs are requested now, so that their DRAM latency overlaps the cdf work
+  float in_a = 0.f, in_b = 0.f;
+  if (fast && lane < n_fine) {
+    if (lane < n_imp) {
+      in_a = __ldg(fine_u + (size_t)r * n_imp + lane);
+      in_b = __ldg(fine_jit + (size_t)r * n_imp + lane);
+    } else {
+      in_a = __ldg(depth_nrm + (size_t)r * n_dep + (lane - n_imp));
+      in_b = __ldg(depth + r);
+    }
+  }
   // coarse samples go into the sort buffer; padding is +inf
-  for (int k = lane; k < Kpad; k += 32) buf[k] = k < Kc ? z_coarse[(size_t)r * Kc + k] : CUDART_INF_F;
+  bool sorted = true;
+  for (int k = lane; k < Kpad; k += 32) {
+    const float zk = k < Kc ? z_coarse[(size_t)r * Kc + k] : CUDART_INF_F;
+    buf[k] = zk;
+  }
   if (n_imp > 0) {
     // pdf = (w + 1e-5) / sum ; cdf = [0, cumsum(pdf)]                          nerf.py:129-133
     float s = 0.f;
@@ -313,33 +351,77 @@ sample_fine_sorted_kernel(const float* __restrict__ rays, const float* __restric
       s += w;
     }
     s = warp_sum(s);
+    for (int k = lane; k < Kc; k += 32) cdf[k + 1] = __fdiv_rn(cdf[k + 1], s);
     __syncwarp();
-    if (lane == 0) {  // sequential cumsum, like torch.cumsum on one row
+    if (lane == 0) {  // sequential running sum, like torch.cumsum on one row
       float c = 0.f;
       cdf[0] = 0.f;
-      for (int k = 1; k <= Kc; ++k) {
-        c = __fadd_rn(c, __fdiv_rn(cdf[k], s));
+      int k = 1;
+      for (; k + 7 <= Kc; k += 8) {  // loads in flight together, adds in order
+        float p[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p[i] = cdf[k + i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          c = __fadd_rn(c, p[i]);
+          cdf[k + i] = c;
+        }
+      }
+      for (; k <= Kc; ++k) {
+        c = __fadd_rn(c, cdf[k]);
         cdf[k] = c;
       }
     }
     __syncwarp();
-    for (int j = lane; j < n_imp; j += 32) {
-      float ind = cdf_bin(cdf, Kc + 1, fine_u[(size_t)r * n_imp + j]);
-      // z_steps = (inds + rand) / n_coarse                                     nerf.py:141
-      float zs = __fdiv_rn(__fadd_rn(ind, fine_jit[(size_t)r * n_imp + j]), (float)Kc);
-      buf[Kc + j] = lerp_depth(near, far, zs, lindisp);
-    }
   }
-  if (n_dep > 0) {
-    float d = depth[r];
-    for (int j = lane; j < n_dep; j += 32) {
+  // the n_fine new samples: lane j (j, j+32, ...) computes sample j
+  float mine = CUDART_INF_F;
+  for (int j = lane; j < n_fine; j += 32) {
+    float v;
+    if (j < n_imp) {
+      float ind = cdf_bin(cdf, Kc + 1, fast ? in_a : fine_u[(size_t)r * n_imp + j]);
+      // z_steps = (inds + rand) / n_coarse                                     nerf.py:141
+      float zs = __fdiv_rn(__fadd_rn(ind, fast ? in_b : fine_jit[(size_t)r * n_imp + j]), (float)Kc);
+      v = lerp_depth(near, far, zs, lindisp);
+    } else {
       // clamp(depth + randn*depth_std, near, far)                              nerf.py:157-160
-      float zz = __fadd_rn(d, __fmul_rn(depth_nrm[(size_t)r * n_dep + j], depth_std));
-      buf[Kc + n_imp + j] = fmaxf(fminf(zz, far), near);
+      float zz = __fadd_rn(fast ? in_b : depth[r], __fmul_rn(fast ? in_a : depth_nrm[(size_t)r * n_dep + (j - n_imp)], depth_std));
+      v = fmaxf(fminf(zz, far), near);
     }
+    if (fast) mine = v; else buf[Kc + j] = v;
   }
   __syncwarp();
-  // bitonic sort of Kpad values, ascending
+  for (int k = lane; k + 1 < Kc; k += 32) sorted = sorted && (buf[k] <= buf[k + 1]);
+  sorted = __all_sync(0xffffffffu, sorted);
+  float* zr = z_out + (size_t)r * K;
+  if (fast && sorted) {
+    // ---- merge by rank: coarse list (Kc, ascending, in buf[0..Kc)) with the sorted new samples (one per lane)
+    const float f = warp_sort32(mine, lane);
+    float* fs = buf + Kc;           // sorted new samples, +inf padded
+    fs[lane] = f;
+    __syncwarp();
+    if (lane < n_fine) {            // position = lane + #(coarse <= f)
+      int lo = 0, hi = Kc;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (buf[mid] <= f) lo = mid + 1; else hi = mid;
+      }
+      zr[lane + lo] = f;
+    }
+    for (int k = lane; k < Kc; k += 32) {  // position = k + #(new < z_k)
+      const float zk = buf[k];
+      int lo = 0, hi = n_fine;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (fs[mid] < zk) lo = mid + 1; else hi = mid;
+      }
+      zr[k + lo] = zk;
+    }
+    return;
+  }
+  if (fast) buf[Kc + lane] = mine;  // (lanes >= n_fine hold +inf: equals the padding)
+  __syncwarp();
+  // general path: bitonic sort of Kpad values in shared memory, ascending
   for (int size = 2; size <= Kpad; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       for (int t = lane; t < (Kpad >> 1); t += 32) {
@@ -355,7 +437,7 @@ sample_fine_sorted_kernel(const float* __restrict__ rays, const float* __restric
       __syncwarp();
     }
   }
-  for (int k = lane; k < K; k += 32) z_out[(size_t)r * K + k] = buf[k];
+  for (int k = lane; k < K; k += 32) zr[k] = buf[k];
 }
 
 int launch_sample_fine_sorted(const float* rays, const float* z_coarse, const float* weights, const float* depth,
@@ -369,16 +451,17 @@ int launch_sample_fine_sorted(const float* rays, const float* z_coarse, const fl
   int Kpad = 2;
   while (Kpad < K) Kpad <<= 1;
   PNR_UNSUPPORTED(Kpad > 2048, "sample_fine: more than 2048 samples per ray");
+  const int Kbuf = Kpad > Kc + 32 ? Kpad : Kc + 32;
   int wpb = 8;
-  size_t smem = (size_t)wpb * (Kc + 1 + Kpad) * sizeof(float);
+  size_t smem = (size_t)wpb * (Kc + 1 + Kbuf) * sizeof(float);
   while (smem > 48 * 1024 && wpb > 1) {
     wpb >>= 1;
-    smem = (size_t)wpb * (Kc + 1 + Kpad) * sizeof(float);
+    smem = (size_t)wpb * (Kc + 1 + Kbuf) * sizeof(float);
   }
   PNR_UNSUPPORTED(smem > 48 * 1024, "sample_fine: per-ray sample count too large for shared memory");
   sample_fine_sorted_kernel<<<ceil_div(B, wpb), wpb * 32, smem, st>>>(rays, z_coarse, weights, depth, fine_u,
                                                                      fine_jitter, depth_normal, B, Kc, n_imp, n_dep,
-                                                                     depth_std, lindisp, Kpad, z_out);
+                                                                     depth_std, lindisp, Kpad, Kbuf, z_out);
   PNR_LAUNCHED();
   return PNR_OK;
 }

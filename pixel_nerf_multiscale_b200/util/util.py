@@ -222,3 +222,11 @@ def finalize_frames(rgb, target=None):
         N.check(N.lib().pnr_finalize_rgb(N.ptr(x), N.ptr(gt), x.numel(), N.ptr(u8), N.ptr(sse), N.stream_ptr(x.device)),
                 "pnr_finalize_rgb")
     return u8, (None if sse is None else -10.0 * torch.log10(sse / x.numel()))
+
+
+def assemble_frames(rgb, depth, n_views, height, width, z_near, z_far):
+    """Frame assembly of the eval drivers on the tensors' own device (eval/eval.py:278-292,
+    eval/gen_video.py:219-222): flat per-ray outputs -> rgb (NV,H,W,3) clamped to [0,1] and the normalised
+    depth image (NV,H,W) = (depth - z_near) / (z_far - z_near) -- no per-batch .cpu() round trip."""
+    rgb = torch.clamp(rgb.reshape(n_views, height, width, 3), 0.0, 1.0)
+    return rgb, normalize_depth(depth.reshape(n_views, height, width), z_near, z_far)

@@ -144,6 +144,64 @@ def test_fine_indices_bit_exact_given_cdf():
     assert torch.equal(inds.cpu(), ref)
 
 
+def _sample_fine_sorted(rays, z_c, w, depth, u, jit, nrm, Kc, n_fine, n_dep, depth_std=0.01):
+    from pixel_nerf_multiscale_b200 import _native as N
+
+    B = rays.shape[0]
+    out = torch.empty(B, Kc + n_fine, device="cuda")
+    c = lambda t: None if t is None else t.cuda().contiguous()
+    keep = [c(t) for t in (rays, z_c, w, depth, u, jit, nrm)]
+    N.check(N.lib().pnr_sample_fine_sorted(*[N.ptr(t) for t in keep], B, Kc, n_fine, n_dep, depth_std, 0, N.ptr(out),
+                                           N.stream_ptr(out.device)), "sample_fine_sorted")
+    return out.cpu()
+
+
+@pytest.mark.parametrize("Kc,n_dep,unsorted", [(64, 32, False), (64, 16, False), (64, 48, False), (120, 8, False),
+                                               (64, 32, True), (33, 1, False)])
+def test_sample_fine_sort_and_merge_bit_exact(Kc, n_dep, unsorted):
+    """cat + sort of nerf.py:286-295 with depth-guided samples only (their arithmetic is elementwise, so the
+    sorted result must be BIT-equal to torch.sort): the merge-by-rank fast path (<= 32 new samples, with and
+    without padding lanes), the general bitonic path (> 32) and the fallback for a coarse list that is not
+    ascending, incl. ties between coarse and new samples."""
+    torch.manual_seed(11 + Kc + n_dep)
+    B = 2048
+    near, far = 0.5, 4.5
+    rays = torch.zeros(B, 8)
+    rays[:, 6], rays[:, 7] = near, far
+    z_c = po.sample_coarse(rays, Kc, False, torch.rand(B, Kc))
+    if unsorted:
+        z_c[::3, [5, 6]] = z_c[::3, [6, 5]]          # an inversion in every third ray
+    depth = near + (far - near) * torch.rand(B)
+    nrm = torch.randn(B, n_dep)
+    depth[::5] = z_c[::5, 7]                          # exact ties between a coarse and a new sample
+    nrm[::5, 0] = 0.0
+    got = _sample_fine_sorted(rays, z_c, None, depth, None, None, nrm, Kc, n_dep, n_dep)
+    ref, _ = torch.sort(torch.cat([z_c, po.sample_fine_depth(rays, depth, 0.01, nrm)], dim=-1), dim=-1)
+    assert torch.equal(got, ref)
+
+
+def test_sample_fine_importance_vs_oracle():
+    """Full sample_fine + sample_fine_depth + sort against the oracle on the CPU (sequential cumsum, like the
+    reference on its CPU path).  The sum of the pdf is accumulated in another order than torch.sum, so a cdf
+    entry may differ in its last bit and move a sample sitting exactly on a bin edge: all but a vanishing share
+    of rays must be bit-equal."""
+    torch.manual_seed(5)
+    B, Kc, n_fine, n_dep = 4096, 64, 32, 16
+    rays = torch.zeros(B, 8)
+    rays[:, 6], rays[:, 7] = 0.8, 1.8
+    z_c = po.sample_coarse(rays, Kc, False, torch.rand(B, Kc))
+    w = torch.rand(B, Kc) ** 6
+    w[::9] = 0.0
+    depth = 0.8 + torch.rand(B)
+    u, jit, nrm = torch.rand(B, n_fine - n_dep), torch.rand(B, n_fine - n_dep), torch.randn(B, n_dep)
+    got = _sample_fine_sorted(rays, z_c, w, depth, u, jit, nrm, Kc, n_fine, n_dep)
+    ref, _ = torch.sort(torch.cat([z_c, po.sample_fine(rays, w, Kc, False, u, jit), po.sample_fine_depth(rays, depth, 0.01, nrm)], -1), -1)
+    same = (got == ref).all(dim=-1)
+    print("rays bit-equal to the oracle: %d / %d" % (int(same.sum()), B))
+    assert same.float().mean().item() > 0.995
+    assert (got[:, 1:] >= got[:, :-1]).all()
+
+
 def test_errors_are_loud():
     net, conf, scene, raw = build_product("ss_ns1", precision="fp32")
     with pytest.raises(RuntimeError):

@@ -158,7 +158,7 @@ def test_gen_video_runs_unmodified_on_the_dropin(tmp_path, precision, tol_levels
     diff = np.abs(frames.astype(np.int32) - ref_u8.astype(np.int32))
     print("gen_video.py (%s): |frame - oracle| in levels of 255: max %d, p99.9 %.1f, mean %.4f, share > %d: %.5f" % (
         precision, diff.max(), np.percentile(diff, 99.9), diff.mean(), tol_levels, (diff > tol_levels).mean()))
-    assert np.percentile(diff, 99.9) <= tol_levels and diff.mean() < 0.5
+    assert np.percentile(diff, 99.9) <= tol_levels and diff.mean() < (1.5 if precision == "bf16" else 0.5)
     assert frames.std() > 5.0   # a real image, not a constant
 
 

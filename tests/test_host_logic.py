@@ -169,3 +169,23 @@ def test_checkpoint_compatibility(tmp_path):
     bad["mlp_coarse.lin_z.0.weight"] = torch.zeros(512, 512)
     with pytest.raises(RuntimeError, match="use_multi_scale"):
         normalize_state_dict(bad, sd)
+
+
+def test_output_tail_helpers():
+    """Frame assembly / depth normalisation (eval.py:278-292) and the small driver-side helpers."""
+    import numpy as np
+
+    import pixel_nerf_multiscale_b200 as pk
+
+    g = torch.Generator().manual_seed(0)
+    rgb, depth = torch.rand(2 * 3 * 4, 3, generator=g) * 1.4 - 0.2, torch.rand(2 * 3 * 4, generator=g) * 3 + 1.2
+    frames, dn = pk.util.assemble_frames(rgb, depth, 2, 3, 4, 1.2, 4.0)
+    ref_rgb = np.clip(rgb.reshape(2, 3, 4, 3).numpy(), 0.0, 1.0)
+    ref_d = ((depth - 1.2) / (4.0 - 1.2)).reshape(2, 3, 4).numpy()
+    assert np.array_equal(frames.numpy(), ref_rgb) and np.allclose(dn.numpy(), ref_d, atol=1e-7)
+    q = torch.tensor([[0.9698, 0.2121, 0.1203, -0.0039], [0.7020, 0.1578, 0.4525, 0.5268]])
+    R = pk.util.quat_to_rot(q)
+    assert torch.allclose(R @ R.transpose(1, 2), torch.eye(3).expand(2, 3, 3), atol=1e-6)
+    assert torch.allclose(pk.util.quat_to_rot(pk.util.rot_to_quat(R)), R, atol=1e-5)
+    assert torch.equal(pk.util.coord_from_blender() @ pk.util.coord_to_blender(), torch.eye(4))
+    assert pk.util.get_cuda(0).type in ("cuda", "cpu")
