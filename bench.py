@@ -79,7 +79,9 @@ def workload_config(name):
     return {"workload": "%s: %s; %s, rays sharded over the ranks, <= %d-ray batches, 64 coarse + 32 fine (16 depth) samples, "
                         "2 MLPs (the CPU reference arm times a bounded ray sample of the same frames per step)"
                         % (name, wl["desc"], per, RAY_BATCH),
-            "points_per_ray": POINTS_PER_RAY}
+            "points_per_ray": POINTS_PER_RAY,
+            "l2": "inputs larger than L2: the per-step working set (samples, per-point outputs: > 0.5 GB) far exceeds the 126 MB "
+                  "L2 and consecutive steps render different frames; no explicit flush"}
 
 
 def rerandomise(mlp, seed):
@@ -627,7 +629,6 @@ def main():
             "collective": ("ncclAllGather (torch.distributed all_gather_into_tensor) of the packed (rgb, depth) rows, %d B per step, "
                            "inside the timed region; source-view state broadcast once before it" % (R * 16)) if world > 1 else
                           "none at N=1 (same frame loop; the all-gather is skipped for a single rank)",
-            "l2": "per-step working set (operand scratch + samples, > 1 GB) far exceeds the 126 MB L2; consecutive steps render different frames",
             "clocks": res["clocks"],
             "e2e": {"value": res["e2e"], "unit": unit, "h2d_bytes_per_step": R * 8 * 4, "d2h_bytes_per_step": R * 4 * 4},
             "gpu_launches": res["launches"], "roofline": roofline(res, peaks), "weak": res.get("weak"),

@@ -42,9 +42,9 @@ def _render(renderer, net, rays, tape, lo=0, hi=None):
     return renderer(net, rays[None, lo:hi], want_weights=True, taps=True)
 
 
-@pytest.mark.parametrize("workload", ["c2", "c4"])
-def test_fullsize_bf16_properties(workload):
-    wl, net, renderer, rays = _scene(workload, "bf16")
+@pytest.mark.parametrize("workload,precision", [("c2", "fp16"), ("c3", "fp16"), ("c4", "fp16"), ("c4", "bf16")])
+def test_fullsize_bf16_properties(workload, precision):
+    wl, net, renderer, rays = _scene(workload, precision)
     n = 50000
     rays = rays[:n].contiguous()
     tape = _tape(n, 11, rays.device)
