@@ -15,7 +15,13 @@ KEYS = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
         "launch__shared_mem_per_block_dynamic", "sm__icc_request_hit_rate.pct", "gcc__cache_requests_type_instruction.sum",
         "gcc__cache_requests_type_instruction.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
-        "lts__t_bytes.sum", "lts__t_sectors_srcunit_tex_op_read.sum", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct"]
+        "lts__t_bytes.sum", "lts__t_sectors_srcunit_tex_op_read.sum", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+        # the L1TEX data pipe (one 128-B wavefront per cycle and SM): LSU side (global/local loads, TMA fills = "lgds",
+        # LDS/STS = "shared") and tensor-core operand reads from shared memory
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts.avg",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_bank_reads.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_writes.avg.pct_of_peak_sustained_elapsed"]
 
 
 def rows_of(rep):
