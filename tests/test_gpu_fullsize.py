@@ -102,3 +102,31 @@ def test_fullsize_bf16_vs_oracle_on_cuda(workload, gain, precision):
     assert r["fine_rgb_p999"] < 1e-2 and r["fine_depth_p999"] < 1e-2
     assert r["fine_rgb_max"] < 5e-2 and r["fine_depth_max"] < 0.15
     assert abs(r["dpsnr"]) <= 0.05 and r["psnr_ours_vs_ref"] > 55.0
+
+
+@pytest.mark.parametrize("workload", ["c3", "c4", "c1"])
+def test_workspace_canaries_untouched(workload):
+    """compute-sanitizer is closed on this pool, so out-of-bounds writes into the caller's scratch are looked for
+    with guard regions: the workspace handed to pnr_render_rays sits between two 1 MiB canaries that must come
+    back untouched after full-size renders (operand ring, staging buffer, sample / output arrays all live in it)."""
+    wl, net, renderer, rays = _scene(workload, "fp16")
+    n = min(50000, rays.shape[0])
+    rays = rays[:n].contiguous()
+    guard = 1 << 20
+    state = {}
+
+    def guarded(nbytes, device):
+        big = torch.empty(int(nbytes) + 2 * guard, dtype=torch.uint8, device=device)
+        big[:guard] = 0xA5
+        big[guard + int(nbytes):] = 0x5A
+        state["big"], state["n"] = big, int(nbytes)
+        return big[guard:guard + int(nbytes)]
+
+    net.workspace = guarded
+    tape = _tape(n, 3, rays.device)
+    with torch.no_grad():
+        for lo, hi in ((0, n), (0, 4097), (n - 333, n)):
+            _render(renderer, net, rays, tape, lo, hi)
+            torch.cuda.synchronize()
+            big, nb = state["big"], state["n"]
+            assert bool((big[:guard] == 0xA5).all()) and bool((big[guard + nb:] == 0x5A).all()), "canary overwritten"
