@@ -26,8 +26,10 @@ __global__ void sample_coarse_kernel(const float* __restrict__ rays, const float
   if (i >= n) return;
   long long r = i / Kc;
   int k = (int)(i - r * Kc);
-  // torch.linspace(0, 1-step, Kc): first half start + step*k, second half end - step*(Kc-1-k)
-  float s = (k < Kc / 2) ? __fmul_rn(lin_step, (float)k) : __fsub_rn(lin_end, __fmul_rn(lin_step, (float)(Kc - 1 - k)));
+  // torch.linspace(0, 1-step, Kc): first half start + step*k, second half end - step*(Kc-1-k).  torch evaluates the
+  // second form as ONE fused multiply-add on the CPU (AVX2/AVX-512 kernels) and on CUDA alike; with a separate
+  // multiply the last bit differs whenever step = (1-1/Kc)/(Kc-1) is inexact (any Kc that is not a power of two)
+  float s = (k < Kc / 2) ? __fmul_rn(lin_step, (float)k) : __fmaf_rn(-lin_step, (float)(Kc - 1 - k), lin_end);
   s = __fadd_rn(s, __fmul_rn(jitter[i], step));
   z[i] = lerp_depth(rays[r * 8 + 6], rays[r * 8 + 7], s, lindisp);
 }

@@ -111,7 +111,9 @@ def run_case(case_name, variants):
 VARIANTS = {
     "ss_ns1": {"default": {}, "lindisp": {"lindisp": True}, "coarse_only": {"n_fine": 0, "n_fine_depth": 0},
                "no_depth": {"n_coarse": 32, "n_fine": 16, "n_fine_depth": 0},
-               "video": {"n_coarse": 64, "n_fine": 128, "n_fine_depth": 16}},
+               "video": {"n_coarse": 64, "n_fine": 128, "n_fine_depth": 16},
+               # a sample count that is not a power of two: torch.linspace's step is then inexact (pins its fused form)
+               "kc48": {"n_coarse": 48, "n_fine": 24, "n_fine_depth": 8}},
     "ms_ns2": {"default": {}},
     "dtu_ns3": {"default": {}},
     "ms_ns3_sb2": {"default": {}},
