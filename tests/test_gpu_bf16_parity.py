@@ -53,7 +53,7 @@ def _bf16_ref_mlp(sd, zx, d_latent, n_blocks, combine_layer, dims, dtype=torch.b
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
-@pytest.mark.parametrize("ns,p", [(1, 64), (2, 37), (3, 200), (1, 300), (3, 41), (4, 50), (5, 77), (7, 33)])
+@pytest.mark.parametrize("ns,p", [(1, 64), (2, 37), (3, 200), (1, 300), (3, 41), (4, 50), (5, 77), (7, 33), (8, 130), (16, 21), (32, 70)])
 def test_mlp_rows_bf16(ns, p, precision):
     from pixel_nerf_multiscale_b200 import _native as N
 

@@ -1,8 +1,8 @@
 """
 Randomised sweep over the conf schema the path reads: feature / code switches (use_xyz, normalize_z,
 use_code, num_freqs, include_input, freq_factor, use_viewdirs, use_code_viewdirs), MLP shape (n_blocks,
-combine_layer incl. "never pooled"), encoder width (num_layers 3/4, single / multi-scale: d_latent 128 / 256 / 512),
-views per object 1..8, objects per call 1..2, sampling (odd n_coarse, n_fine 0 / <= 32 / > 32, depth samples,
+combine_layer incl. "never pooled"), encoder width (num_layers 3/4/5, single / multi-scale: d_latent 128 .. 1024),
+views per object 1..16, objects per call 1..2, sampling (odd n_coarse, n_fine 0 / <= 32 / > 32, depth samples,
 lindisp, white background) and tiny ray counts (1 ray: fewer tiles than cluster pairs).  Every configuration is
 rendered by the fp32 validation path (bar 1e-4) and by the tensor-core path with f16 operands (bar 1e-2 at
 identical sample positions) and compared with the oracle on the same device and the same random draws.
@@ -19,7 +19,7 @@ from oracle import synth
 from sigma_sweep import Replay
 
 pytestmark = pytest.mark.gpu
-N_CONFIGS = 40
+N_CONFIGS = 48
 
 
 def _draw(i):
@@ -29,16 +29,17 @@ def _draw(i):
     m = dict(use_xyz=r.random() < 0.75, normalize_z=r.random() < 0.6, use_code=use_code, use_viewdirs=use_viewdirs,
              use_code_viewdirs=use_viewdirs and r.random() < 0.5,
              code=dict(num_freqs=r.choice([2, 4, 6, 10]), include_input=r.random() < 0.7, freq_factor=r.choice([1.5, 3.14159265])))
-    n_blocks = r.choice([1, 2, 3, 5, 6])
-    ns = r.choice([1, 1, 2, 3, 3, 4, 5, 6, 8])
+    n_blocks = r.choice([1, 2, 3, 5, 6, 8])
+    ns = r.choice([1, 1, 2, 3, 3, 4, 5, 6, 8, 11, 16])
     combine = r.randint(1, n_blocks) if n_blocks > 1 else 1
     if ns == 1 and r.random() < 0.4:
         combine = 1000                       # the single-view base schema: never pooled
     if combine >= n_blocks and ns > 1:
-        n_blocks = combine + 1               # multi-view rows need a pooling point inside the network
-    num_layers = r.choice([3, 4])
+        combine = n_blocks - 1 if n_blocks > 1 else 1
+        n_blocks = max(n_blocks, combine + 1)   # multi-view rows need a pooling point inside the network
+    num_layers = r.choice([3, 4, 4, 5])
     multi = r.random() < 0.5
-    chans = [64, 64, 128, 256][:num_layers]
+    chans = [64, 64, 128, 256, 512][:num_layers]
     sizes = [(r.randint(5, 14), r.randint(5, 14)) for _ in chans]
     levels = [(c, h, w) for c, (h, w) in zip(chans, sizes)] if multi else [(chans[-1],) + sizes[-1]]
     sb = r.choice([1, 1, 2])
