@@ -130,3 +130,32 @@ def test_workspace_canaries_untouched(workload):
             torch.cuda.synchronize()
             big, nb = state["big"], state["n"]
             assert bool((big[:guard] == 0xA5).all()) and bool((big[guard + nb:] == 0x5A).all()), "canary overwritten"
+
+
+@pytest.mark.parametrize("workload", ["c2", "c4"])
+def test_net_forward_many_points_vs_oracle(workload):
+    """PixelNeRFNet.forward on explicit points (the recon / direct-query entry, models.py.backup2:155-282) at a size
+    that spans many tiles and groups per cluster pair: 40 000 points of the full-size scene against the oracle."""
+    import bench
+    from oracle import pixelnerf_oracle as po
+
+    wl, net, renderer, rays = _scene(workload, "fp16")
+    dev = rays.device
+    n = 40000
+    g = torch.Generator().manual_seed(9)
+    pick = torch.randint(0, rays.shape[0], (n,), generator=g).to(dev)
+    t = torch.rand(n, 1, generator=g).to(dev)
+    r = rays[pick]
+    xyz = (r[:, :3] + (r[:, 6:7] * (1 - t) + r[:, 7:8] * t) * r[:, 3:6])[None].contiguous()
+    vd = r[:, 3:6][None].contiguous()
+    conf = bench.load_conf(wl)
+    gscene = bench.oracle_scene(net, None, conf, device=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        for coarse in (True, False):
+            out = net(xyz, coarse=coarse, viewdirs=vd)
+            ref = po.net_forward(gscene, xyz, coarse=coarse, viewdirs=vd)
+            e_rgb = (out[..., :3] - ref[..., :3]).abs().max().item()
+            e_sig = (out[..., 3] - ref[..., 3]).abs().max().item()
+            print("%s net.forward(coarse=%s) 40 000 points: rgb %.2e sigma %.2e (sigma max %.2f)" % (workload, coarse, e_rgb, e_sig, ref[..., 3].max().item()))
+            assert e_rgb < 2e-3 and e_sig < 1e-2 * max(1.0, ref[..., 3].max().item())

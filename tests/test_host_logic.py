@@ -60,6 +60,15 @@ def test_unsupported_configs_fail_loudly():
     c["model"].put("use_global_encoder", True)
     with pytest.raises(NotImplementedError):
         pk.make_model(c["model"])
+    # sampling options of SpatialEncoder.index the native gather does not implement (encoder.py:182-188)
+    for key, val in (("index_interp", "nearest"), ("index_padding", "zeros")):
+        c = _conf("dtu.conf")
+        c["model"]["encoder"].put(key, val)
+        net = pk.make_model(c["model"]).eval()
+        with torch.no_grad():
+            net.encode(torch.zeros(1, 1, 3, 32, 32), torch.eye(4)[None, None], torch.tensor(30.0))
+        with pytest.raises(NotImplementedError):
+            net.native_scene()
 
 
 def test_encode_bookkeeping_matches_oracle():
