@@ -52,7 +52,7 @@ constexpr int B_CHUNK = 128 * KS * 2;   // 16 KB: [8 k-groups][128 n-rows][8 bf1
 constexpr int A_SLICE = ROWS * KS * 2;  // 8 KB : [8 k-groups][64 rows][8 bf16]
 constexpr int NB_ST = 6;                // unified operand ring: weight chunks (16 KB) and [latent|code] slices (8 KB)
 #ifndef PNR_RING_A
-#define PNR_RING_A NB_ST                // experiment knob: ring slots phase A actually uses (<= NB_ST); 4/5/6 -> 632k/654k/665k rays/s on C2
+#define PNR_RING_A NB_ST                // experiment knob: ring slots actually used (<= NB_ST); 4/5/6 -> 632k/654k/665k rays/s on C2
 #endif
 #ifndef PNR_B_SPLIT
 #define PNR_B_SPLIT 2
@@ -93,7 +93,7 @@ struct Params {
   int apply_head;
   int* err;
   unsigned long long* stats;           // optional [pairs][16] cycle counters (debug)
-  // in-kernel gather (warps 2-3 of phase A produce the operand image one tile ahead of the MMAs)
+  // in-kernel gather (warps 2-3 produce the operand image of the next A tile one tile ahead of the MMAs)
   int fused_gather;                    // 0: zc was written by rows_to_operand_kernel (pnr_mlp_forward)
   int zc_ring;                         // > 0 (fused gather): zc holds zc_ring (2) tiles per cluster pair, reused round-robin,
                                        // so the image stays in L2 and is never written back to DRAM; 0: one slot per tile
@@ -107,7 +107,7 @@ struct Params {
 using namespace tc;
 
 // ---------------------------------------------------------------------------------------------
-// row <-> point mapping of a phase-A tile: CTA c, row r (0..63): point-in-CTA pl = r / ns, view
+// row <-> point mapping of an A tile: CTA c, row r (0..63): point-in-CTA pl = r / ns, view
 // v = r % ns; rows with pl >= ppc (= 64 / ns) are padding.  A point's rows are adjacent TMEM lanes; for
 // ns that do not divide 32 one point straddles the two 32-lane groups (handled in the pool epilogue).
 // ---------------------------------------------------------------------------------------------
@@ -232,7 +232,7 @@ int mlp_tc_pack(const pnr_mlp& m, void* dst, size_t dst_bytes, int fmt, cudaStre
     PNR_TRY(pack(m.fc1_w[b], DH, DH / 64, L.off_g3[b]));
   }
   // bias tables.  biasA[b]: constant to add to the TMEM residual when it is read before block b of
-  // phase A (the GEMMs accumulate without biases); biasA[n_pre] is the pooled output's constant.
+  // the A tiles (the GEMMs accumulate without biases); biasA[n_pre] is the pooled output's constant.
   float* biasA = (float*)(d + L.off_biasA);
   float* biasB = (float*)(d + L.off_biasB);
   float* bias0 = (float*)(d + L.off_bias0);
@@ -329,7 +329,7 @@ __device__ __forceinline__ Taps make_taps_fast(float u, float v, int H, int W, f
   return t;
 }
 
-// Per-lane variant used by the gather warps inside phase A: lane = one row of the tile; the lane loops
+// Gather warps of the fused kernel: lane = one row of the tile; the lane loops
 // over the 8-channel groups (4 scattered 128-bit tap loads each; adjacent groups share 32-B sectors
 // through L1) and over the code groups, and writes 16-byte operand entries -- a warp stores 512
 // contiguous bytes per group.
@@ -461,9 +461,9 @@ rows_to_operand_kernel(const float* __restrict__ zx, int d_latent, int d_in, int
 #define PROD_SYNC() __syncwarp()
 #define PROD_ENTER() true
 #endif
-// The issuer's mode is a template parameter (SM) of its helpers and of the phase-A kernel: solo is ~2 % faster
-// where the fc GEMMs dominate (L = 256: C2, C3) and ~4 % slower on the multi-scale L = 512 schema (C4),
-// measured A/B on one box; net_forward_tc picks by latent width.  Phase B always runs solo.
+// The issuer's mode is a template parameter (SM) of its helpers and of the fused kernel: solo is 1.5 % faster
+// where the fc GEMMs dominate (L = 256: c3 458 vs 451 k rays/s) and 0.8 % slower on the multi-scale L = 512 schema
+// (c4 384 vs 387 k), measured A/B on one box with the fused kernel; run_fused picks by latent width.
 template <bool SM> __device__ __forceinline__ bool mma_elect() { if constexpr (SM) return true; else return elect_one(); }
 template <bool SM> __device__ __forceinline__ void mma_sync() { if constexpr (!SM) __syncwarp(); }
 template <bool SM> __device__ __forceinline__ bool mma_enter() { if constexpr (SM) return elect_one(); else return true; }
