@@ -585,6 +585,18 @@ def main():
             torch.cuda.empty_cache()
         r5 = measure_c5(cx, 6, 3, args.c5_views)
         legs["c5"] = r5
+        if args.precision == "fp16":
+            # the same default workload with bf16 operands (north_star's literal operand format; see DESIGN section 2 for why
+            # f16 operands are the default): same kernels, same MMA rate, lower multiplier energy under the power cap
+            cx.precision = "bf16"
+            r = measure(cx, wl_name, k, 3, profile=True)
+            roof = roofline(r, {}) if rank == 0 else None
+            legs[wl_name + "_bf16_operands"] = {"value": r["value"], "unit": unit, "e2e": r["e2e"], "steps": k, "ms_per_step": r["ms"] / k,
+                                                "rays_per_step": r["rays_per_step"], "dtype": "bf16",
+                                                "fused_mlp_TFLOPs": roof["achieved"] if roof else None}
+            cx.precision = args.precision
+            del r
+            torch.cuda.empty_cache()
 
     if rank == 0:
         peaks = {}

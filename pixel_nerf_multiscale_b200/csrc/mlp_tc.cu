@@ -499,6 +499,20 @@ __device__ __forceinline__ void twait(Ctx& cx, int cls, uint32_t bar, uint32_t p
 #endif
 }
 
+// Group waits: the 8 epilogue warps (and the 2 gather warps) always wait for the same barrier phase at the same
+// point of their programs.  Every waiting warp polls shared memory (a suspended try_wait comes back a few hundred
+// cycles later), and those polls compete with the TMA fills and the tensor core's operand reads for the
+// shared-memory pipe (spinning instead of suspending costs 14 % of the kernel).  So ONE warp of the group waits on
+// the mbarrier and the others block on a named hardware barrier, which does not poll.
+__device__ __forceinline__ void epi_group_wait(Ctx& cx, int cls, uint32_t bar, uint32_t parity, int tag) {
+  if ((threadIdx.x >> 5) == 4) twait(cx, cls, bar, parity, tag);
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+__device__ __forceinline__ void gather_group_wait(Ctx& cx, int cls, uint32_t bar, uint32_t parity, int tag) {
+  if ((threadIdx.x >> 5) == 2) twait(cx, cls, bar, parity, tag);
+  asm volatile("bar.sync 6, 64;" ::: "memory");
+}
+
 // ---- producer side helpers ----------------------------------------------------------------------
 __device__ __forceinline__ long long* ts_slot(int which, int idx) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -752,7 +766,7 @@ __device__ __noinline__ long long pool_tile(const Params& p, Ctx cx, const Epi e
   for (int nb = 0; nb < 2; ++nb) {
     BiasRegs bp;
     prefetch_bias(bp, e, bP, nb);
-    twait(cx, 0, cx.bar(X_READY + nb), xph, 405 + nb * 1000 + (int)it * 10000);
+    epi_group_wait(cx, 0, cx.bar(X_READY + nb), xph, 405 + nb * 1000 + (int)it * 10000);
     tc_fence_after();
     const long long tq0 = clock64();
 #pragma unroll
@@ -894,7 +908,7 @@ __device__ __noinline__ void head_tile(const Params& p, Ctx cx, const Epi e, uin
     BiasRegs bo;
     prefetch_bias(bo, e, bO, nb);
     if (wait_x) {
-      mbar_wait(cx.bar(X_READY + nb), xph, cx.err, 505);
+      epi_group_wait(cx, 0, cx.bar(X_READY + nb), xph, 505);
       tc_fence_after();
     }
 #pragma unroll
@@ -1089,7 +1103,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
         // issued every load of tile git-2, and the ring slots those loads used have been recycled since (so they
         // have landed): once ZC_TAKEN(git-1) completed the slot is free.  The gather therefore runs exactly one
         // tile ahead of the MMAs, and the image (2 x 2 x nsl x 8 KB per pair) stays resident in L2.
-        if (git >= 1) twait(cx, 2, cx.bar(ZC_TAKEN), (git - 1) & 1, 204);
+        if (git >= 1) gather_group_wait(cx, 2, cx.bar(ZC_TAKEN), (git - 1) & 1, 204);
         const size_t zslot = p.zc_ring ? (size_t)pair * p.zc_ring + git % p.zc_ring : (size_t)tile;
         uint8_t* base = const_cast<uint8_t*>(p.zc) + ((zslot * 2 + cx.rank) * nsl) * A_SLICE + (size_t)row * 16;
         gather_row_to_zc<FMT>(p.sc, p.xyz, p.viewdirs, p.rays, p.zsamp, p.K, gp, v, valid, p.nks_z, p.nks_c, base);
@@ -1117,7 +1131,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
           BiasRegs br;
           for (int nb = 0; nb < 2; ++nb) {
             prefetch_bias(br, e, biasA + (size_t)b * DH, nb);
-            twait(cx, 0, cx.bar(X_READY + nb), xph, 401 + nb * 1000 + (int)tc * 10000 + warp * 1000000 + (int)cx.rank * 100000000);
+            epi_group_wait(cx, 0, cx.bar(X_READY + nb), xph, 401 + nb * 1000 + (int)tc * 10000 + (int)cx.rank * 100000000);
             tc_fence_after();
             t0 = clock64();
             epi_to_operand<FMT>(cx, e, xcol, nb, br, OFF_SX, SX_READY);
@@ -1126,7 +1140,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
           xph ^= 1;
           for (int nb = 0; nb < 2; ++nb) {
             prefetch_bias(br, e, bias0 + (size_t)b * DH, nb);
-            twait(cx, 1, cx.bar(NET_READY + nb), nph, 402 + nb);
+            epi_group_wait(cx, 1, cx.bar(NET_READY + nb), nph, 402 + nb);
             tc_fence_after();
             t0 = clock64();
             epi_to_operand<FMT>(cx, e, netcol, nb, br, OFF_H, H_READY);
@@ -1164,7 +1178,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
           BiasRegs br;
           for (int nb = 0; nb < 2; ++nb) {
             prefetch_bias(br, e, bias0 + (size_t)b * DH, nb);
-            twait(cx, 1, cx.bar(NET_READY + nb), nph, 502 + nb);
+            epi_group_wait(cx, 1, cx.bar(NET_READY + nb), nph, 502 + nb);
             tc_fence_after();
             epi_to_operand<FMT>(cx, e, netcol, nb, br, OFF_H, H_READY);
           }
@@ -1172,7 +1186,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
           if (j + 1 < p.n_post) {
             for (int nb = 0; nb < 2; ++nb) {
               prefetch_bias(br, e, biasB + (size_t)(j + 1) * DH, nb);
-              twait(cx, 0, cx.bar(X_READY + nb), xph, 501);
+              epi_group_wait(cx, 0, cx.bar(X_READY + nb), xph, 501);
               tc_fence_after();
               epi_to_operand<FMT>(cx, e, xcol, nb, br, OFF_SX, SX_READY);
             }
