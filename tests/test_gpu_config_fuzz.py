@@ -8,6 +8,7 @@ rendered by the fp32 validation path (bar 1e-4) and by the tensor-core path with
 identical sample positions) and compared with the oracle on the same device and the same random draws.
 The seeds are fixed: the sweep is deterministic.
 """
+import os
 import random
 
 import pytest
@@ -19,7 +20,7 @@ from oracle import synth
 from sigma_sweep import Replay
 
 pytestmark = pytest.mark.gpu
-N_CONFIGS = 48
+N_CONFIGS = int(os.environ.get("PNR_FUZZ_CONFIGS", "48"))   # a longer one-off sweep: PNR_FUZZ_CONFIGS=300
 
 
 def _draw(i):
