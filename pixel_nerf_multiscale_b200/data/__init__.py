@@ -4,7 +4,7 @@ Dataset adapters behind ``get_split_dataset`` -- the data side of the reference'
 train/train.py).  The reference imports ``from data import get_split_dataset`` but its own ``src/data``
 package is ABSENT from the tree, so these adapters restate the on-disk formats of upstream pixelNeRF
 (SRN cars/chairs folders, DVR / NMR ShapeNet renders, the DVR-format DTU set) from the contract the
-callers rely on; they are pinned by round-trip tests on synthetic on-disk fixtures
+callers rely on (plus the two-object ``multi_obj`` scenes in NeRF-synthetic layout); they are pinned by round-trip tests on synthetic on-disk fixtures
 (tests/test_data_adapters.py), not by reference goldens ("parity unpinned": nothing to compare with).
 
 What every item is (the drivers index it as ``dset[i]`` or through a DataLoader with batch_size=1):
@@ -23,7 +23,7 @@ import os
 import numpy as np
 import torch
 
-__all__ = ["get_split_dataset", "SRNDataset", "DVRDataset"]
+__all__ = ["get_split_dataset", "SRNDataset", "DVRDataset", "MultiObjectDataset"]
 
 _FLIP_YZ = torch.diag(torch.tensor([1.0, -1.0, -1.0, 1.0]))  # OpenCV camera (y down, z forward) <-> (y up, z back)
 
@@ -236,10 +236,53 @@ class DVRDataset(torch.utils.data.Dataset):
         return item
 
 
+class MultiObjectDataset(torch.utils.data.Dataset):
+    """Two-object ShapeNet scenes in NeRF-synthetic layout: ``<path>/<stage>/<scene>/transforms.json`` with
+    ``camera_angle_x`` and ``frames[{file_path, transform_matrix}]`` (camera-to-world, already in the renderer's
+    convention), RGBA PNGs next to it (composited on white; the alpha channel is the mask)."""
+
+    def __init__(self, path, stage="train", z_near=4.0, z_far=9.0, n_views=None):
+        super().__init__()
+        base = os.path.join(path, stage)
+        assert os.path.exists(base), "multi_obj split directory %s does not exist" % base
+        self.scenes = sorted(os.path.dirname(x) for x in glob.glob(os.path.join(base, "*", "transforms.json")))
+        self.stage, self.n_views = stage, n_views
+        self.z_near, self.z_far, self.lindisp = z_near, z_far, False
+
+    def __len__(self):
+        return len(self.scenes)
+
+    def __getitem__(self, index):
+        import cv2
+        import json
+
+        root = self.scenes[index]
+        with open(os.path.join(root, "transforms.json"), "r") as f:
+            meta = json.load(f)
+        frames = meta["frames"]
+        if self.n_views is not None and self.n_views < len(frames):
+            frames = [frames[i] for i in np.sort(np.random.choice(len(frames), self.n_views, replace=False))]
+        images, masks, bboxes, poses = [], [], [], []
+        for fr in frames:
+            fpath = os.path.join(root, os.path.basename(fr["file_path"]) + ".png")
+            raw = cv2.imread(fpath, cv2.IMREAD_UNCHANGED)
+            if raw is None:
+                raise FileNotFoundError(fpath)
+            fg = raw[..., 3] > 127 if raw.shape[2] == 4 else np.ones(raw.shape[:2], dtype=bool)
+            images.append(_to_tensor_balanced(_read_rgb(fpath)))
+            masks.append(torch.from_numpy(fg.astype(np.float32))[None])
+            bboxes.append(_bbox_of(fg))
+            poses.append(torch.tensor(fr["transform_matrix"], dtype=torch.float32))
+        images = torch.stack(images)
+        focal = 0.5 * images.shape[-1] / np.tan(0.5 * float(meta["camera_angle_x"]))
+        return {"path": root, "img_id": index, "focal": torch.tensor(focal, dtype=torch.float32), "images": images,
+                "masks": torch.stack(masks), "bbox": torch.stack(bboxes), "poses": torch.stack(poses)}
+
+
 def get_split_dataset(dataset_type, datadir, want_split="all", training=True, **kwargs):
     """
     Dataset(s) of the requested split.
-    :param dataset_type  srn | dvr | dvr_gen | dvr_dtu
+    :param dataset_type  srn | multi_obj | dvr | dvr_gen | dvr_dtu
     :param want_split    train | val | test | all (-> (train, val, test))
     :param training      only affects augmentation / image caps of upstream's training mode
     """
@@ -255,7 +298,7 @@ def get_split_dataset(dataset_type, datadir, want_split="all", training=True, **
             if training:
                 flags["max_imgs"] = 49
     elif dataset_type == "multi_obj":
-        raise NotImplementedError("multi_obj (two-object ShapeNet scenes) is not provided; formats: srn, dvr, dvr_gen, dvr_dtu")
+        cls = MultiObjectDataset
     else:
         raise NotImplementedError("Unsupported dataset type %r" % (dataset_type,))
     flags.update(kwargs)

@@ -96,3 +96,35 @@ def test_dvr_shapenet_and_dtu_round_trip(tmp_path):
     assert item["images"].shape == (2, 3, 30, 40)
     assert np.allclose(item["poses"].numpy(), np.stack(want), atol=1e-4)
     assert abs(float(item["focal"]) - 72.3) < 1e-3 and torch.allclose(item["c"], torch.tensor([20.0, 15.0]), atol=1e-3)
+
+
+def test_multi_obj_round_trip(tmp_path):
+    import json
+
+    import cv2
+
+    import pixel_nerf_multiscale_b200 as pk
+    from pixel_nerf_multiscale_b200.data import get_split_dataset
+
+    g = np.random.RandomState(2)
+    root = os.path.join(str(tmp_path), "two_obj", "val", "scene_000")
+    os.makedirs(root)
+    want, imgs, frames = [], [], []
+    for v in range(3):
+        pose = pk.util.pose_spherical(50.0 * v, -25.0, 6.0)
+        rgba = g.randint(0, 255, size=(24, 24, 4)).astype(np.uint8)
+        rgba[..., 3] = np.where(g.rand(24, 24) > 0.5, 255, 0)
+        cv2.imwrite(os.path.join(root, "r_%d.png" % v), rgba[..., [2, 1, 0, 3]])
+        frames.append({"file_path": "./r_%d" % v, "transform_matrix": pose.tolist()})
+        want.append(pose.numpy())
+        a = rgba[..., 3:4].astype(np.float32) / 255.0
+        imgs.append((rgba[..., :3].astype(np.float32) * a + 255.0 * (1 - a)).astype(np.uint8))
+    json.dump({"camera_angle_x": 0.7, "frames": frames}, open(os.path.join(root, "transforms.json"), "w"))
+    dset = get_split_dataset("multi_obj", os.path.join(str(tmp_path), "two_obj"), want_split="val", training=False)
+    item = dset[0]
+    assert len(dset) == 1 and (dset.z_near, dset.z_far, dset.lindisp) == (4.0, 9.0, False)
+    assert np.allclose(item["poses"].numpy(), np.stack(want), atol=1e-6)
+    assert abs(float(item["focal"]) - 0.5 * 24 / np.tan(0.35)) < 1e-4
+    u8 = ((item["images"].permute(0, 2, 3, 1) * 0.5 + 0.5) * 255).round().numpy().astype(np.uint8)
+    assert np.array_equal(u8, np.stack(imgs))
+    assert item["masks"].shape == (3, 1, 24, 24) and item["bbox"].shape == (3, 4)
