@@ -159,3 +159,20 @@ def test_net_forward_many_points_vs_oracle(workload):
             e_sig = (out[..., 3] - ref[..., 3]).abs().max().item()
             print("%s net.forward(coarse=%s) 40 000 points: rgb %.2e sigma %.2e (sigma max %.2f)" % (workload, coarse, e_rgb, e_sig, ref[..., 3].max().item()))
             assert e_rgb < 2e-3 and e_sig < 1e-2 * max(1.0, ref[..., 3].max().item())
+
+
+@pytest.mark.parametrize("workload", ["c3", "c4"])
+def test_soak_bit_identical_renders(workload):
+    """40 renders of the same 50 000-ray batch with the same random draws must be bit-identical: a rare race in
+    the fused kernel's hand-offs (operand ring, staging buffer, TMEM halves, group waits) would show up as a
+    changed checksum."""
+    wl, net, renderer, rays = _scene(workload, "fp16")
+    n = 50000
+    rays = rays[:n].contiguous()
+    tape = _tape(n, 21, rays.device)
+    with torch.no_grad():
+        first = _render(renderer, net, rays, tape)
+        ref = (first.fine.rgb.clone(), first.fine.depth.clone(), first.coarse.rgb.clone())
+        for i in range(40):
+            out = _render(renderer, net, rays, tape)
+            assert torch.equal(out.fine.rgb, ref[0]) and torch.equal(out.fine.depth, ref[1]) and torch.equal(out.coarse.rgb, ref[2]), i
