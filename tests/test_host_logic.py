@@ -198,3 +198,21 @@ def test_output_tail_helpers():
     assert torch.allclose(pk.util.quat_to_rot(pk.util.rot_to_quat(R)), R, atol=1e-5)
     assert torch.equal(pk.util.coord_from_blender() @ pk.util.coord_to_blender(), torch.eye(4))
     assert pk.util.get_cuda(0).type in ("cuda", "cpu")
+
+
+def test_bench_step_definitions():
+    """bench.py: every workload's steps cover whole frames (or whole 50 000-ray batches of the orbit), and both arms
+    print the same config."""
+    import bench
+
+    for name, wl in bench.WORKLOADS.items():
+        rng = bench.step_ranges(wl)
+        per = wl["W"] * wl["H"]
+        assert rng and all(hi > lo for lo, hi in rng) and rng[-1][1] <= wl["video_frames"] * per
+        if wl["step"] == "batch":
+            assert all(hi - lo == bench.RAY_BATCH for lo, hi in rng)
+        else:
+            assert all(hi - lo == per and lo % per == 0 for lo, hi in rng)
+        cfg = bench.workload_config(name)
+        assert cfg["workload"].startswith(name + ":") and "l2" in cfg and cfg == bench.workload_config(name)
+    assert bench.workload_config("c3")["workload"].startswith("c3: DTU 300x400")
